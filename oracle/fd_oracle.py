@@ -7,9 +7,9 @@ getMseReward :235-270, getState :272-286, analytic :289-291).
 
 The reference builds a dense N x N matrix M and evaluates ``M @ u``; every row of M
 has at most three non-zeros (sub-diagonal, diagonal, super-diagonal, periodic), so the
-oracle forms the same three products per row.  A dense matvec sums the N products of a
-row left to right with N-3 exact zeros in between, hence the oracle adds the three
-non-zero terms in COLUMN order to stay bit-comparable (rows 0 and N-1 wrap).
+oracle forms the same three products per row and adds them in column order (the
+remaining N-3 products are exact zeros).  BLAS may associate the three terms
+differently, so agreement with the reference is to an ulp, not bitwise.
 """
 import numpy as np
 
@@ -124,7 +124,8 @@ class AdvectionOracle:
     def step(self, actions=None):
         """Advection.py:154-213.  ``actions``: None (Lax), [B, 2] (one global stencil:
         a0 multiplies u_{k-1}, a1 multiplies u_{k+1}) or [B, 2N] (per point: entry 2j
-        multiplies u_{k+1}, entry 2j+1 multiplies u_{k-1} -- the opposite convention)."""
+        multiplies u_{k+1}, entry 2j+1 multiplies u_{k-1} -- the opposite convention --
+        except in the last row k = N-1, where the reference swaps them again)."""
         u = self.u
         one = np.ones((self.B, self.N))
         if actions is None:
@@ -135,8 +136,10 @@ class AdvectionOracle:
                 lo, up = a[:, 0:1] * one, a[:, 1:2] * one
                 di = (1 - (a[:, 0:1] + a[:, 1:2])) * one      # 1 - sum(actions) (:165)
             else:
-                up, lo = a[:, 0::2], a[:, 1::2]
+                up, lo = a[:, 0::2].copy(), a[:, 1::2].copy()
                 di = 1.0 - up - lo                            # (:182)
+                # the last row swaps the convention: even entry -> u_{N-2}, odd -> u_0 (:188-190)
+                up[:, -1], lo[:, -1] = a[:, -1], a[:, -2]
         self.u = _tri_matvec(lo, di, up, u)
         self.t += self.dt
         self.ioutnum += 1

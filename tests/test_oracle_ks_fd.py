@@ -142,10 +142,10 @@ def test_known_answers():
         d0.step(); d1.step(np.array([[-2.0]]))
     assert rel(d0.u, d1.u) < 1e-13
     assert rel(d0.u, d0.analytic()) < 1e-3
-    a0 = AdvectionOracle(N=N, L=L, dt=1e-3, nu=1.0); a0.IC(np.sin(x)[None])
-    a1 = AdvectionOracle(N=N, L=L, dt=1e-3, nu=1.0); a1.IC(np.sin(x)[None])
+    a0 = AdvectionOracle(N=N, L=L, dt=0.09, nu=1.0); a0.IC(np.sin(x)[None])     # Courant ~0.92
+    a1 = AdvectionOracle(N=N, L=L, dt=0.09, nu=1.0); a1.IC(np.sin(x)[None])
     al = a0.alpha
-    for _ in range(100):
+    for _ in range(20):
         a0.step(); a1.step(np.array([[0.5 + 0.5 * al, 0.5 - 0.5 * al]]))
     assert rel(a0.u, a1.u) < 1e-13
-    assert rel(a0.u[0], a0.analytic()) < 0.3     # Lax is very diffusive at alpha << 1
+    assert rel(a0.u[0], a0.analytic()) < 2e-2
