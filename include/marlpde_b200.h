@@ -1,0 +1,151 @@
+/*
+ * marlpde_b200 -- C ABI of the B200-native marlpde environment time-stepper.
+ *
+ * The reference (wadaniel/marlpde) has no FFI: its hot path is the duck-typed Python
+ * class API of python/_model/{Burger,KS,Diffusion,Advection}.py, driven one environment
+ * and one step per call by python/_model/*_environment.py.  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point names the
+ * reference method(s) it replaces for a BATCH of B independent environments.
+ *
+ * Conventions
+ *   - plain C, no torch types: device buffers are raw CUDA device pointers, `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream);
+ *   - all per-call buffers are CALLER-owned device memory, row-major with the environment
+ *     index first ([B, ...]); the library owns only the persistent solver state allocated
+ *     in mpde_create and freed in mpde_destroy;
+ *   - element type of real buffers is double (dtype MPDE_F64) or float (MPDE_F32); complex
+ *     buffers are interleaved (re, im) pairs of that type;
+ *   - every call is asynchronous on `stream`, does no allocation and no synchronisation
+ *     (CUDA-graph capturable), except create/destroy/set_* which may synchronise;
+ *   - return value 0 = success, negative = error (message via mpde_last_error()).
+ *     A numerical blow-up is NOT an error: it sets status[e] = MPDE_TRUNCATED and freezes
+ *     environment e (reference: np.seterr(over='raise') + the try/except of
+ *     burger_environment.py:158-167,198-201).
+ */
+#ifndef MARLPDE_B200_H
+#define MARLPDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPDE_ABI_VERSION 1
+
+enum mpde_equation { MPDE_BURGERS = 0, MPDE_KS = 1, MPDE_DIFFUSION = 2, MPDE_ADVECTION = 3 };
+enum mpde_dtype { MPDE_F64 = 0, MPDE_F32 = 1 };
+enum mpde_status { MPDE_RUNNING = 0, MPDE_TRUNCATED = 1 };
+enum mpde_reward { MPDE_REWARD_NONE = 0, MPDE_REWARD_SPECTRAL = 1, MPDE_REWARD_MSE = 2, MPDE_REWARD_DIRECT = 3 };
+
+/* configuration flags (constructor keywords of the reference classes) */
+#define MPDE_DFORCE   (1 << 0) /* Burger/KS(dforce=True): actions are a direct forcing          */
+#define MPDE_FORCING  (1 << 1) /* Burger(forcing=True): 3-mode stochastic forcing                */
+#define MPDE_SSM      (1 << 2) /* Burger(ssm=True): static Smagorinsky closure                   */
+#define MPDE_DSM      (1 << 3) /* Burger(dsm=True): dynamic Smagorinsky closure                  */
+#define MPDE_IMPLICIT (1 << 4) /* Diffusion(implicit=True): implicit-Euler FDstep                */
+
+/* fields for mpde_get / mpde_set */
+enum mpde_field {
+    MPDE_FIELD_U = 0,       /* [B,N] real      current field  (Burger.u, KS: Re ifft(v))                 */
+    MPDE_FIELD_V = 1,       /* [B,N] complex   current spectrum, FFT order (Burger.v / KS.v)             */
+    MPDE_FIELD_FN_OLD = 2,  /* [B,N] complex   Burger.Fn_old                                             */
+    MPDE_FIELD_U_PREV = 3,  /* [B,N] real      uu[ioutnum-1]                                             */
+    MPDE_FIELD_EK_SUM = 4,  /* [B,N/2+1] float32  running sum of Ek_kt rows (Ek_ktt * (ioutnum+1))       */
+    MPDE_FIELD_IOUTNUM = 5, /* [B] int32                                                                 */
+    MPDE_FIELD_T = 6,       /* [B] real        accumulated time                                          */
+    MPDE_FIELD_KPREV = 7,   /* [B] real        kPrevRelErr of the spectral reward                        */
+    MPDE_FIELD_STATUS = 8,  /* [B] int32                                                                 */
+    MPDE_FIELD_K = 9,       /* [N] real        wavenumber table (Burger.k)                               */
+    MPDE_FIELD_NU = 10      /* [B] real                                                                  */
+};
+
+typedef struct mpde_config {
+    int32_t struct_size;  /* = sizeof(mpde_config)                                                 */
+    int32_t equation;     /* enum mpde_equation                                                    */
+    int32_t dtype;        /* enum mpde_dtype                                                       */
+    int32_t device;       /* CUDA device ordinal                                                   */
+    int64_t nenvs;        /* B                                                                     */
+    int32_t N;            /* grid points (power of two for the spectral solvers)                   */
+    int32_t M;            /* actions per environment (0 = none yet; mpde_set_basis may change it)  */
+    int32_t num_agents;   /* A (numAgents); must divide N                                          */
+    int32_t version;      /* Burger state version 0..4 (Burger.py:617-626)                         */
+    int32_t stepper;      /* s: forcing column period (Burger.py:416)                              */
+    int32_t flags;        /* MPDE_DFORCE | MPDE_FORCING | ...                                      */
+    int32_t reward_mode;  /* enum mpde_reward                                                      */
+    int32_t reserved;
+    double L;             /* domain length                                                         */
+    double dt;            /* time step                                                             */
+} mpde_config;
+
+typedef struct mpde_env mpde_env;
+
+/* Burger.__init__/__setup_fourier (Burger.py:24-175), KS.__init__ (KS.py:33-137),
+ * Diffusion/Advection.__init__: allocate the batched solver state and constant tables. */
+int mpde_create(const mpde_config* cfg, mpde_env** out);
+int mpde_destroy(mpde_env* env);
+
+/* number of reals per environment written by mpde_step(state_out): len(getState()) */
+int64_t mpde_state_size(const mpde_env* env);
+
+/* viscosity per environment (Burger.nu incl. nunoise, Burger.py:87-89); host array of n = 1 or B */
+int mpde_set_nu(mpde_env* env, const double* nu_host, int64_t n);
+
+/* setup_basis (Burger.py:177-203 / KS.py:139-164): HOST row-major [M,N] basis matrix.  May be
+ * called at any time (the reference sets the basis after construction); synchronises. */
+int mpde_set_basis(mpde_env* env, int32_t M, const double* basis_host);
+
+/* which reward mpde_step(reward_out) evaluates (enum mpde_reward) */
+int mpde_set_reward_mode(mpde_env* env, int32_t mode);
+
+/* KS.__setup_etdrk4 tables (KS.py:127-137): HOST arrays of N doubles each, FFT order */
+int mpde_set_etdrk4(mpde_env* env, const double* E, const double* E2, const double* Q,
+                    const double* f1, const double* f2, const double* f3);
+
+/* Stochastic forcing (Burger.py:410-421): HOST complex table [n, stepper, 3] (n = 1 or B) holding
+ * fft(forcing)[k] for k = 1,2,3 and each column c = ioutnum % stepper:
+ *   r1[k,c] * sqrt(2)/L / sqrt(k*s*dt) * (N/2) * exp(i*(2 pi k offset / L + 2 pi r2[k,c])) */
+int mpde_set_forcing(mpde_env* env, const double* coef_host, int64_t n);
+
+/* Spectral-reward reference (burger_environment.py:174): DEVICE double [nref, rows, N/2] rows of
+ * dns.Ek_ktt[:, :N/2]; env_map DEVICE int32 [B] or NULL (all environments use reference 0). */
+int mpde_set_spectrum_ref(mpde_env* env, const double* ek_dev, int64_t nref, int64_t rows, const int32_t* env_map_dev);
+
+/* setGroundTruth + getMseReward (Burger.py:322-323, 578-601): DEVICE real [ntruth, rows, N] table of
+ * the truth interpolated at the (shifted) grid of the environments, one row per solver step. */
+int mpde_set_truth(mpde_env* env, const void* truth_dev, int64_t ntruth, int64_t rows, const int32_t* env_map_dev);
+
+/* Optional per-step history (Burger.py:151-152, 497-498, 555): caller-owned DEVICE buffers, each may
+ * be NULL: uu [B, rows, N] real, vv [B, rows, N] complex64, ektt [B, rows, N/2+1] double
+ * (= Ek_ktt[:, :N/2+1], the running time-average of the float32 spectrum rows).
+ * Row i is written when an environment reaches ioutnum == i (row 0 by reset). */
+int mpde_set_history(mpde_env* env, void* uu_dev, void* vv_dev, double* ektt_dev, int64_t rows);
+
+/* IC(u0=...) / IC(v0=...) (Burger.py:205-320, KS.py:166-219): DEVICE [B,N] real or complex.
+ * mask_dev: DEVICE uint8 [B] (1 = reset this environment) or NULL = all. */
+int mpde_reset_u(mpde_env* env, const void* u0_dev, const uint8_t* mask_dev, void* stream);
+int mpde_reset_v(mpde_env* env, const void* v0_dev, const uint8_t* mask_dev, void* stream);
+
+/* step(actions) x nsub + getState + reward (Burger.py:333-499, 604-675; KS.py:230-274, 369-383;
+ * Diffusion.py:164-216; Advection.py:154-213; burger_environment.py:148-176).
+ *   actions_dev : [B, M] real or NULL (step() without actions)
+ *   nsub        : solver steps with these actions held fixed (nIntermediate); 0 = getState only
+ *   state_out   : [B, mpde_state_size] real or NULL
+ *   reward_out  : [B, A] real or NULL
+ * status is kept in the library (MPDE_FIELD_STATUS). */
+int mpde_step(mpde_env* env, const void* actions_dev, int32_t nsub, void* state_out, void* reward_out, void* stream);
+
+/* attribute access (u, v, Fn_old, ioutnum, t, ...): DEVICE destination / source of the natural shape */
+int mpde_get(mpde_env* env, int32_t field, void* dst_dev, void* stream);
+int mpde_set(mpde_env* env, int32_t field, const void* src_dev, void* stream);
+
+/* introspection for the bench: kernels launched so far by this handle */
+int64_t mpde_launch_count(const mpde_env* env);
+
+const char* mpde_last_error(void);
+int mpde_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLPDE_B200_H */

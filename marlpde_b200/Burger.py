@@ -1,0 +1,449 @@
+"""Batched, GPU-resident drop-in for the reference ``Burger`` environment class.
+
+Mirrors the public API of /root/reference/python/_model/Burger.py (constructor keywords
+:24-44, ``setup_basis`` :177, ``IC`` :205, ``setGroundTruth`` :322, ``step`` :333,
+``simulate`` :501, ``compute_Ek`` :541, ``getMseReward`` :578, ``getState`` :604) for
+``nenvs`` independent environments that live on one B200.  With ``nenvs=1`` the methods
+return exactly what the reference returns (nested lists / numpy); with ``nenvs>1`` they
+return device tensors with the environment index first.
+
+Only host-side set-up (initial conditions, forcing tables, basis, truth interpolation) is
+computed here with numpy; every ``step`` runs in the CUDA library (marlpde_b200/csrc).
+"""
+import numpy as np
+import torch
+
+from . import _lib as LB
+from ._base import BatchedEnv
+from .hostmath import (grid_points, fft_wavenumbers, make_basis, turbulence_field, forced_field,
+                       forcing_spectrum_coefficients, TruthInterpolant)
+
+
+class Burger(BatchedEnv):
+    equation = LB.BURGERS
+
+    def __init__(self, L=2. * np.pi, N=1024, dt=0.001, nu=0.02, dforce=True, ssmforce=False, nsteps=None,
+                 tend=5., u0=None, v0=None, case=None, forcing=False, ssm=False, dsm=False, noise=0., seed=42,
+                 version=0, nunoise=False, numAgents=1, s=1, *, nenvs=1, device=None, dtype=torch.float64,
+                 history=None, offset=None):
+        assert not (ssm and dsm)                                            # Burger.py:50
+        if ssmforce and not dforce:
+            raise SystemExit("[Burger] SSM forcing requires dforce")      # Burger.py:113-115
+        B = int(nenvs)
+        self.numAgents = numAgents
+        self.L, self.dt, self.tend = float(L), float(dt), float(tend)
+        nsteps = int(tend / dt) if nsteps is None else int(nsteps)
+        self.N, self.dx = N, L / N
+        self.x = grid_points(self.L, N)
+        self.nsteps = self.nout = nsteps
+        self.stepper = int(s)
+        self.forcing, self.ssm, self.dsm = bool(forcing), bool(ssm), bool(dsm)
+        self.dforce, self.ssmforce = bool(dforce), bool(ssmforce)
+        self.version, self.cs = version, 0.1
+        self.M, self.basis, self.f_truth = 0, None, None
+
+        # per-environment seeds; offset ~ N(0, noise*L) redrawn until |offset| <= L (Burger.py:53-57;
+        # the reference draws it from an UNSEEDED generator -- pass offset= to pin it)
+        self.seeds = np.broadcast_to(np.asarray(seed, dtype=np.int64), (B,)).copy()
+        self.tseed = self.seeds
+        self.noise = noise * L
+        if offset is not None:
+            off = np.broadcast_to(np.asarray(offset, dtype=np.float64), (B,)).copy()
+        elif self.noise > 0.:
+            rng = np.random.default_rng()
+            off = rng.normal(0., self.noise, B)
+            while np.any(np.abs(off) > L):
+                bad = np.abs(off) > L
+                off[bad] = rng.normal(0., self.noise, int(bad.sum()))
+        else:
+            off = np.zeros(B)
+        self._offset = off
+
+        # seeded stream: [nunoise uniform] -> randfac1 -> randfac2 -> ('forced' IC draws) (Burger.py:66,88-95)
+        nus = np.full(B, float(nu))
+        self._streams = {}
+        need_tables = self.forcing or case == 'forced' or nunoise
+        uniq = np.unique(self.seeds)
+        r1 = r2 = None
+        if need_tables:
+            per_seed = {}
+            for sd in uniq:
+                rs = np.random.RandomState(int(sd))
+                nu_s = 0.01 + 0.02 * rs.uniform() if nunoise else float(nu)
+                a = rs.normal(loc=0., scale=1., size=(32, nsteps))
+                b = rs.normal(loc=0., scale=1., size=(32, nsteps))
+                per_seed[int(sd)] = (nu_s, a, b)
+                self._streams[int(sd)] = rs
+            if nunoise:
+                nus = np.array([per_seed[int(sd)][0] for sd in self.seeds])
+            if len(uniq) == 1:
+                r1, r2 = per_seed[int(uniq[0])][1:]
+            else:   # keep only the columns the stepper can ever index (ioutnum % s, Burger.py:416)
+                r1 = np.stack([per_seed[int(sd)][1][:, :self.stepper] for sd in self.seeds])
+                r2 = np.stack([per_seed[int(sd)][2][:, :self.stepper] for sd in self.seeds])
+        self._randfac1, self._randfac2 = r1, r2
+        self._nu = nus
+        self._forcing_dirty = True
+
+        flags = (L_DFORCE if dforce else 0) | (L_FORCING if forcing else 0) | (L_SSM if ssm else 0) | (L_DSM if dsm else 0)
+        self._create(nenvs=B, N=N, L_=self.L, dt=self.dt, M=0, num_agents=numAgents, version=version,
+                     stepper=self.stepper, flags=flags, device=device, dtype=dtype)
+        L_check(self._lib.mpde_set_nu(self._h, LB.as_dp(np.ascontiguousarray(self._nu)), B))
+
+        self.k = fft_wavenumbers(self.L, N)                                # Burger.py:161-163
+        self.k1 = 1j * self.k
+        self.k2 = self.k1 ** 2
+
+        self._setup_history(history)
+        self._state_buf = torch.empty((B, self._state_size), device=self.device, dtype=self.dtype)
+        self._reward_buf = torch.zeros((B, numAgents), device=self.device, dtype=self.dtype)
+        self._state_at = self._reward_at = -1
+        self._spec_ref = None
+        self._truth_shift = None
+
+        if case is not None:
+            self.IC(case=case)
+        elif u0 is None and v0 is None:
+            self.IC()
+        elif u0 is not None:
+            self.IC(u0=u0)
+        else:
+            self.IC(v0=v0)
+
+    # ------------------------------------------------------------------ simple attributes
+    @property
+    def nu(self):
+        return float(self._nu[0]) if self.nenvs == 1 else self._nu
+
+    @property
+    def offset(self):
+        return float(self._offset[0]) if self.nenvs == 1 else self._offset
+
+    @offset.setter
+    def offset(self, value):
+        self._offset = np.broadcast_to(np.asarray(value, dtype=np.float64), (self.nenvs,)).copy()
+        self._forcing_dirty = True
+
+    @property
+    def randfac1(self):
+        return self._randfac1
+
+    @randfac1.setter
+    def randfac1(self, value):           # the environment copies the DNS tables (burger_environment.py:99-100)
+        self._randfac1 = np.asarray(value)
+        self._forcing_dirty = True
+
+    @property
+    def randfac2(self):
+        return self._randfac2
+
+    @randfac2.setter
+    def randfac2(self, value):
+        self._randfac2 = np.asarray(value)
+        self._forcing_dirty = True
+
+    def _squeeze(self, t):
+        return t[0] if self.nenvs == 1 else t
+
+    @property
+    def u(self):
+        return self._squeeze(self._get(LB.FIELD_U, (self.nenvs, self.N), self.dtype))
+
+    @property
+    def v(self):
+        return self._squeeze(self._get(LB.FIELD_V, (self.nenvs, self.N), self.cdtype))
+
+    @property
+    def Fn_old(self):
+        return self._squeeze(self._get(LB.FIELD_FN_OLD, (self.nenvs, self.N), self.cdtype))
+
+    # ------------------------------------------------------------------ history
+    def _setup_history(self, history):
+        B, rows, N = self.nenvs, self.nout + 1, self.N
+        per_row = N * (torch.empty((), dtype=self.dtype).element_size() + 8) + (N // 2 + 1) * 8
+        if history is None:
+            history = B * rows * per_row <= (2 << 30)
+        self.history = bool(history)
+        self.tt = np.concatenate(([0.], np.cumsum(np.full(self.nout, self.dt))))   # t += dt (Burger.py:494,499)
+        if self.history:
+            self._uu = torch.zeros((B, rows, N), device=self.device, dtype=self.dtype)
+            self._vv = torch.zeros((B, rows, N), device=self.device, dtype=torch.complex64)
+            self._ektt = torch.zeros((B, rows, N // 2 + 1), device=self.device, dtype=torch.float64)
+            L_check(self._lib.mpde_set_history(self._h, self._ptr(self._uu), self._ptr(self._vv),
+                                               self._ptr(self._ektt), rows))
+        else:
+            self._uu = self._vv = self._ektt = None
+            L_check(self._lib.mpde_set_history(self._h, None, None, None, 0))
+
+    @property
+    def uu(self):
+        self._need_history()
+        return self._squeeze(self._uu)
+
+    @property
+    def vv(self):
+        self._need_history()
+        return self._squeeze(self._vv)
+
+    def _need_history(self):
+        if not self.history:
+            raise RuntimeError("history recording is off for this batch (pass history=True)")
+
+    # ------------------------------------------------------------------ set-up
+    def setup_basis(self, M, kind='uniform'):
+        """Burger.py:177-203."""
+        self.M = M
+        self.basis = make_basis(self.x, self.L, M, kind)
+        L_check(self._lib.mpde_set_basis(self._h, int(M), LB.as_dp(np.ascontiguousarray(self.basis))))
+
+    def IC(self, u0=None, v0=None, case='zero', mask=None):
+        """Burger.py:205-320.  u0 / v0: [N] (shared) or [B, N]; ``mask`` resets a subset."""
+        B, N = self.nenvs, self.N
+        if v0 is None:
+            if u0 is None:
+                u0 = self._case_field(case)
+            else:
+                if np.shape(u0)[-1] != N:
+                    raise SystemExit(f"[Burger] Error: wrong IC array size (is {np.shape(u0)[-1]}, expected {N}")
+            u0d = self._batch(u0, self.dtype, (N,))
+            m, mp = self._mask_ptr(mask)
+            L_check(self._lib.mpde_reset_u(self._h, self._ptr(u0d), mp, self._stream()))
+        else:
+            if np.shape(v0)[-1] != N:
+                raise SystemExit(f"[Burger] Error: wrong IC array size (is {np.shape(v0)[-1]}, expected {N}")
+            v0d = self._batch(v0, self.cdtype, (N,))
+            m, mp = self._mask_ptr(mask)
+            L_check(self._lib.mpde_reset_v(self._h, self._ptr(torch.view_as_real(v0d)), mp, self._stream()))
+        self.t = 0.
+        self.stepnum = 0
+        self.ioutnum = 0
+        self._state_at = self._reward_at = -1
+        self.u0 = self.u
+        self.v0 = self.v
+
+    def _case_field(self, case):
+        B, N = self.nenvs, self.N
+        out = np.empty((B, N))
+        cache = {}
+        for e in range(B):
+            key = (int(self.seeds[e]), float(self._offset[e]))
+            if key not in cache:
+                if case == 'sinus':                                        # Burger.py:224
+                    f = np.sin(4. * np.pi * (self.x + key[1]) / self.L)
+                elif case == 'turbulence':                                 # Burger.py:227-260
+                    f = turbulence_field(self.x, self.L, N, key[1], key[0])
+                elif case == 'zero':
+                    f = np.zeros(N)
+                elif case == 'forced':                                     # Burger.py:265-273
+                    f = forced_field(self.x, self.L, N, self._streams[key[0]])
+                else:
+                    raise SystemExit("[Burger] Error: IC case unknown")
+                cache[key] = f
+            out[e] = cache[key]
+        return out
+
+    def setGroundTruth(self, x, t, uu_truth):
+        """Burger.py:322-323 (argument order x, t, uu).  The cubic tensor-product spline is
+        built lazily on the host; the device only sees the truth sampled on this grid."""
+        self.f_truth = TruthInterpolant(_np(x), _np(t), _np(uu_truth), kind='cubic')
+        self._truth_shift = None
+
+    def mapGroundTruth(self):
+        t = np.arange(0, self.nout + 1) * self.dt
+        return self.f_truth(self.x, t)
+
+    def set_truth_table(self, table, env_map=None):
+        """Directly provide the truth sampled at this grid: [rows, N] or [ntruth, rows, N]."""
+        tab = self._dev(table)
+        if tab.dim() == 2:
+            tab = tab.unsqueeze(0)
+        mp = None
+        if env_map is not None:
+            self._keep['truth_map'] = self._dev(env_map, torch.int32, (self.nenvs,))
+            mp = self._ptr(self._keep['truth_map'])
+        self._keep['truth'] = tab.contiguous()
+        L_check(self._lib.mpde_set_truth(self._h, self._ptr(self._keep['truth']), tab.shape[0], tab.shape[1], mp))
+        L_check(self._lib.mpde_set_reward_mode(self._h, LB.REWARD_MSE))
+        self._truth_shift = 'explicit'
+
+    def _ensure_truth(self, shift):
+        """Sample the spline at x + shift (wrapped into [0, L], Burger.py:581-588) for every
+        row of tt; environments sharing a shift share a table."""
+        shift = np.broadcast_to(np.asarray(shift, dtype=np.float64), (self.nenvs,))
+        key = shift.tobytes()
+        if self._truth_shift == key or self._truth_shift == 'explicit':
+            return
+        if self.f_truth is None:
+            raise RuntimeError("getMseReward needs setGroundTruth(...) or set_truth_table(...)")
+        uniq, inv = np.unique(shift, return_inverse=True)
+        tabs = []
+        for sh in uniq:
+            newx = self.x + sh
+            newx[newx > self.L] -= self.L
+            newx[newx < 0] += self.L
+            tabs.append(self.f_truth.rows(newx, self.tt))
+        self.set_truth_table(np.stack(tabs), env_map=inv.astype(np.int32) if len(uniq) > 1 else None)
+        self._truth_shift = key
+
+    def set_spectrum_reference(self, ref, env_map=None):
+        """Reference spectrum rows for the spectral reward (burger_environment.py:174):
+        a DNS ``Burger`` with history, or an array [rows, >=N/2] / [nref, rows, >=N/2]."""
+        h = self.N // 2
+        if isinstance(ref, Burger):
+            ref._need_history()
+            tab = ref._ektt[:, :, :h]
+        else:
+            tab = self._dev(ref, torch.float64)
+            if tab.dim() == 2:
+                tab = tab.unsqueeze(0)
+            tab = tab[:, :, :h]
+        tab = tab.to(self.device).contiguous()
+        mp = None
+        if env_map is not None:
+            self._keep['ek_map'] = self._dev(env_map, torch.int32, (self.nenvs,))
+            mp = self._ptr(self._keep['ek_map'])
+        self._keep['ek_ref'] = tab
+        L_check(self._lib.mpde_set_spectrum_ref(self._h, self._ptr(tab), tab.shape[0], tab.shape[1], mp))
+        L_check(self._lib.mpde_set_reward_mode(self._h, LB.REWARD_SPECTRAL))
+        self._spec_ref = tab
+
+    def _upload_forcing(self):
+        if not self.forcing or not self._forcing_dirty:
+            return
+        coef = forcing_spectrum_coefficients(self._randfac1, self._randfac2, self._offset, self.L, self.dt,
+                                             self.stepper, self.N, self.nenvs)
+        L_check(self._lib.mpde_set_forcing(self._h, LB.as_dp(coef), coef.shape[0]))
+        self._forcing_dirty = False
+
+    # ------------------------------------------------------------------ stepping
+    def _actions(self, actions):
+        if actions is None:
+            return None
+        assert self.basis is not None, "[Burger] Basis not set up (is None)."
+        if isinstance(actions, torch.Tensor):
+            a = actions.to(device=self.device, dtype=self.dtype)
+        else:
+            a = torch.as_tensor(np.asarray(actions, dtype=np.float64), device=self.device).to(self.dtype)
+        a = a.reshape(self.nenvs, -1)                                      # MARL lists are flattened (Burger.py:437)
+        assert a.shape[1] == self.M, "[Burger] Wrong number of actions (provided {}/{}".format(a.shape[1], self.M)
+        return a.contiguous()
+
+    def step_n(self, actions=None, n=1, want_state=True, want_reward=True):
+        """``n`` solver steps with the same actions (the inner loop of
+        burger_environment.py:148-155) + getState + reward, as ONE kernel launch.
+        Returns (state [B,S], reward [B,A]) device tensors (None when not requested)."""
+        self._upload_forcing()
+        a = self._actions(actions)
+        st = self._state_buf if want_state else None
+        rw = self._reward_buf if (want_reward and (self._spec_ref is not None or self._truth_shift is not None)) else None
+        L_check(self._lib.mpde_step(self._h, self._ptr(a), int(n), self._ptr(st), self._ptr(rw), self._stream()))
+        self.stepnum += n
+        self.ioutnum += n
+        for _ in range(n):
+            self.t += self.dt                                              # Burger.py:494
+        if st is not None:
+            self._state_at = self.ioutnum
+        if rw is not None:
+            self._reward_at = self.ioutnum
+        return st, rw
+
+    def step(self, actions=None):
+        """Burger.py:333-499: one solver step."""
+        self.step_n(actions, 1, want_state=False, want_reward=self._truth_shift is not None)
+
+    def simulate(self, nsteps=None, restart=False, correction=[]):
+        """Burger.py:501-539 (``correction`` is not supported)."""
+        if len(correction):
+            raise NotImplementedError("simulate(correction=...)")
+        if nsteps is not None:
+            self.nsteps = int(nsteps)
+        if restart:
+            self.nout = self.nsteps
+            self._setup_history(self.history)
+            self.IC(v0=self.v0 if self.nenvs > 1 else self.v0[None])
+        left = self.nsteps
+        while left > 0:
+            n = min(left, 500)
+            self.step_n(None, n, want_state=False, want_reward=False)
+            left -= n
+        if bool((self.status != 0).any()):
+            print("[Burger] Floating point exception occured in simulate", flush=True)
+            return -1
+
+    # ------------------------------------------------------------------ observables
+    def getState(self, nAgents=None, as_tensor=None):
+        """Burger.py:604-675.  nenvs == 1: the reference's nested lists; else [B,S] / [B,A,S/A]."""
+        if self._state_at != self.ioutnum:
+            L_check(self._lib.mpde_step(self._h, None, 0, self._ptr(self._state_buf), None, self._stream()))
+            self._state_at = self.ioutnum
+        A = self.numAgents
+        st = self._state_buf if A == 1 else self._state_buf.view(self.nenvs, A, -1)
+        if as_tensor is None:
+            as_tensor = self.nenvs > 1
+        if as_tensor:
+            return st
+        host = st[0].cpu().numpy()
+        return [host.tolist()] if A == 1 else [row.tolist() for row in host]
+
+    def getMseReward(self, shift=0., as_tensor=None):
+        """Burger.py:578-601 -> rewards per agent; nenvs == 1: numpy [A]."""
+        self._ensure_truth(shift)
+        if self._reward_at != self.ioutnum:
+            L_check(self._lib.mpde_step(self._h, None, 0, None, self._ptr(self._reward_buf), self._stream()))
+            self._reward_at = self.ioutnum
+        if as_tensor is None:
+            as_tensor = self.nenvs > 1
+        return self._reward_buf if as_tensor else self._reward_buf[0].cpu().numpy()
+
+    def Ek_ktt_row(self):
+        """Row ``ioutnum`` of Ek_ktt[:, :N/2+1] (Burger.py:555) from the running float32 sums."""
+        acc = self._get(LB.FIELD_EK_SUM, (self.nenvs, self.N // 2 + 1), torch.float32)
+        cnt = (self.ioutnum_all + 1).to(torch.float64).unsqueeze(1)
+        return self._squeeze(acc.to(torch.float64) / cnt)
+
+    def compute_Ek(self):
+        """Burger.py:541-576 from the recorded history (float32 chain of the complex64 vv)."""
+        self._need_history()
+        i = self.ioutnum
+        vv = self._vv[:, :i + 1]
+        self.Ek_kt = self._squeeze(0.5 * torch.real(vv.conj() * vv / self.N) * np.float32(self.dx))
+        ekt = self.Ek_kt if self.nenvs > 1 else self.Ek_kt[None]
+        self.Ek_k = self._squeeze(ekt.sum(1) / (i + 1))
+        self.Ek_t = self._squeeze(ekt.sum(2))
+        n = self.N
+        half = self._ektt[:, :i + 1]                                       # exact sequential float32 sums
+        idx = torch.arange(n, device=self.device)
+        idx = torch.where(idx <= n // 2, idx, n - idx)
+        self.Ek_ktt = self._squeeze(half[:, :, idx])
+        den = torch.arange(1, i + 2, device=self.device, dtype=torch.float64)
+        self.Ek_tt = self._squeeze(torch.cumsum(ekt.sum(2), 1).to(torch.float64) / den)
+
+    # ------------------------------------------------------------------ checkpoint
+    def state_dict(self):
+        B, N = self.nenvs, self.N
+        return dict(v=self._get(LB.FIELD_V, (B, N), self.cdtype), Fn_old=self._get(LB.FIELD_FN_OLD, (B, N), self.cdtype),
+                    u_prev=self._get(LB.FIELD_U_PREV, (B, N), self.dtype),
+                    ek_sum=self._get(LB.FIELD_EK_SUM, (B, N // 2 + 1), torch.float32),
+                    ioutnum=self._get(LB.FIELD_IOUTNUM, (B,), torch.int32), t=self._get(LB.FIELD_T, (B,), self.dtype),
+                    kprev=self._get(LB.FIELD_KPREV, (B,), self.dtype), status=self._get(LB.FIELD_STATUS, (B,), torch.int32),
+                    host=dict(t=self.t, ioutnum=self.ioutnum, stepnum=self.stepnum))
+
+    def load_state_dict(self, sd):
+        self._set(LB.FIELD_V, torch.view_as_real(sd['v'].to(self.device).contiguous()))
+        self._set(LB.FIELD_FN_OLD, torch.view_as_real(sd['Fn_old'].to(self.device).contiguous()))
+        self._set(LB.FIELD_U_PREV, sd['u_prev'].to(self.device).contiguous())
+        self._set(LB.FIELD_EK_SUM, sd['ek_sum'].to(self.device).contiguous())
+        self._set(LB.FIELD_IOUTNUM, sd['ioutnum'].to(self.device).contiguous())
+        self._set(LB.FIELD_T, sd['t'].to(self.device).contiguous())
+        self._set(LB.FIELD_KPREV, sd['kprev'].to(self.device).contiguous())
+        self._set(LB.FIELD_STATUS, sd['status'].to(self.device).contiguous())
+        self.t, self.ioutnum, self.stepnum = sd['host']['t'], sd['host']['ioutnum'], sd['host']['stepnum']
+        self._state_at = self._reward_at = -1
+
+
+def _np(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
+L_DFORCE, L_FORCING, L_SSM, L_DSM = LB.DFORCE, LB.FORCING, LB.SSM, LB.DSM
+L_check = LB.check

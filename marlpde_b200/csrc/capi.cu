@@ -1,0 +1,476 @@
+// C ABI of marlpde_b200 (see include/marlpde_b200.h).  Host-side handle management and
+// kernel dispatch; no torch, no CPU compute path: every solver call launches sm_100a kernels.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/marlpde_b200.h"
+#include "dispatch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return -1;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+}  // namespace
+
+using namespace mpde;
+
+struct mpde_env {
+    mpde_config cfg{};
+    int64_t launches = 0;
+    virtual ~mpde_env() {}
+    virtual int init() = 0;
+    virtual int set_nu(const double* nu, int64_t n) = 0;
+    virtual int set_basis(int M, const double* basis) = 0;
+    virtual int set_etd(const double* const tabs[6]) = 0;
+    virtual int set_forcing(const double* coef, int64_t n) = 0;
+    virtual int set_spectrum_ref(const double* ek, int64_t nref, int64_t rows, const int32_t* map) = 0;
+    virtual int set_truth(const void* truth, int64_t ntruth, int64_t rows, const int32_t* map) = 0;
+    virtual int set_history(void* uu, void* vv, double* ektt, int64_t rows) = 0;
+    virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
+    virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
+    virtual int get(int field, void* dst, cudaStream_t st) = 0;
+    virtual int set(int field, const void* src, cudaStream_t st) = 0;
+    int64_t state_size() const {
+        const int N = cfg.N, A = cfg.num_agents, ver = cfg.version;
+        if (cfg.equation == MPDE_BURGERS) {
+            const int nf = (ver == 1 || ver == 2) ? 2 : 1;
+            const int seg = A == 1 ? N : N / A + 2;
+            const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
+            return (int64_t)A * (nf * seg + tail);
+        }
+        if (cfg.equation == MPDE_KS) return 2 * N;
+        return A == 1 ? N : (int64_t)A * (N / A + 2);
+    }
+};
+
+template <typename T>
+struct Env : mpde_env {
+    SpectralParams<T> prm{};
+    std::vector<void*> owned;
+    int n_forcing = 0;
+
+    template <typename U>
+    int dalloc(U** p, size_t count) {
+        void* q = nullptr;
+        CU(cudaMalloc(&q, count * sizeof(U) + 16));
+        CU(cudaMemset(q, 0, count * sizeof(U) + 16));
+        owned.push_back(q);
+        *p = static_cast<U*>(q);
+        return 0;
+    }
+    template <typename U>
+    int upload(U* dst, const std::vector<U>& src) {
+        CU(cudaMemcpy(dst, src.data(), src.size() * sizeof(U), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    ~Env() override {
+        for (void* p : owned) cudaFree(p);
+    }
+
+    bool spectral() const { return cfg.equation == MPDE_BURGERS || cfg.equation == MPDE_KS; }
+
+    int init() override {
+        CU(cudaSetDevice(cfg.device));
+        const int N = cfg.N;
+        const int64_t B = cfg.nenvs;
+        prm.B = B;
+        prm.N = N;
+        prm.M = cfg.M;
+        prm.A = cfg.num_agents;
+        prm.version = cfg.version;
+        prm.stepper = cfg.stepper;
+        prm.reward_mode = cfg.reward_mode;
+        prm.dt = (T)cfg.dt;
+        prm.dx = (T)(cfg.L / N);
+        if (spectral()) {
+            // twiddles exp(-2 pi i j / N), j < N/2
+            std::vector<Cx<T>> tw(N / 2);
+            for (int j = 0; j < N / 2; ++j) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * j / N;
+                tw[j].re = (T)cosl(a);
+                tw[j].im = (T)sinl(a);
+            }
+            Cx<T>* dtw;
+            if (dalloc(&dtw, N / 2)) return -1;
+            if (upload(dtw, tw)) return -1;
+            prm.tw = dtw;
+            // scipy.fftpack.fftfreq(N, d) with d = L / (2 pi N) (Burger.py:161): k_n = n * (1 / (N d))
+            const double d = cfg.L / (2 * M_PI * N);
+            const double val = 1.0 / (N * d);
+            std::vector<T> kw(N);
+            for (int n = 0; n < N; ++n) kw[n] = (T)((n < (N + 1) / 2 ? n : n - N) * val);
+            if (N % 2 == 0) kw[N / 2] = (T)(-(N / 2) * val);
+            T* dk;
+            if (dalloc(&dk, N)) return -1;
+            if (upload(dk, kw)) return -1;
+            prm.kwave = dk;
+            const int NH = N / 2 + 1;
+            Cx<T>*v, *fn;
+            float* acc;
+            if (dalloc(&v, B * NH) || dalloc(&fn, B * NH) || dalloc(&acc, B * NH)) return -1;
+            prm.v = v;
+            prm.fn = fn;
+            prm.acc = acc;
+        }
+        T *nu, *tnow, *kprev, *uprev;
+        int *iout, *status;
+        if (dalloc(&nu, B) || dalloc(&tnow, B) || dalloc(&kprev, B) || dalloc(&iout, B) || dalloc(&status, B)) return -1;
+        if (dalloc(&uprev, B * N)) return -1;
+        prm.nu = nu;
+        prm.tnow = tnow;
+        prm.kprev = kprev;
+        prm.iout = iout;
+        prm.status = status;
+        prm.uprev = uprev;
+        {
+            int* ti;
+            T* twt;
+            if (dalloc(&ti, 2 * N) || dalloc(&twt, 2 * N)) return -1;
+            prm.tap_idx = ti;
+            prm.tap_w = twt;
+        }
+        if (cfg.flags & MPDE_FORCING) {
+            Cx<T>* fc;
+            if (dalloc(&fc, (size_t)B * cfg.stepper * 3)) return -1;
+            prm.fcoef = fc;
+        }
+        if (cfg.equation == MPDE_KS) {
+            T* etd;
+            if (dalloc(&etd, (size_t)6 * N)) return -1;
+            prm.etd = etd;
+        }
+        return 0;
+    }
+
+    int set_nu(const double* nu, int64_t n) override {
+        if (n != 1 && n != cfg.nenvs) return fail("set_nu: n must be 1 or nenvs");
+        std::vector<T> h(cfg.nenvs);
+        for (int64_t i = 0; i < cfg.nenvs; ++i) h[i] = (T)nu[n == 1 ? 0 : i];
+        return upload(const_cast<T*>(prm.nu), h);
+    }
+
+    int set_basis(int M, const double* basis) override {
+        const int N = cfg.N;
+        if (M <= 0 || M > 4096) return fail("set_basis: M must be in 1..4096");
+        CU(cudaSetDevice(cfg.device));
+        CU(cudaDeviceSynchronize());
+        if (M != basis_rows) {
+            T* bs;
+            if (dalloc(&bs, (size_t)M * N)) return -1;      // old table stays owned until destroy
+            prm.basis = bs;
+            basis_rows = M;
+        }
+        cfg.M = M;
+        prm.M = M;
+        std::vector<int> idx(2 * N, 0);
+        std::vector<T> w(2 * N, T(0)), dense((size_t)M * N);
+        bool sparse = true;
+        for (int j = 0; j < N; ++j) {
+            int cnt = 0;
+            for (int i = 0; i < M; ++i) {
+                const double b = basis[(size_t)i * N + j];
+                dense[(size_t)i * N + j] = (T)b;
+                if (b != 0.0) {
+                    if (cnt < 2) {
+                        idx[2 * j + cnt] = i;
+                        w[2 * j + cnt] = (T)b;
+                    }
+                    ++cnt;
+                }
+            }
+            if (cnt > 2) sparse = false;
+        }
+        basis_dense = !sparse;
+        if (upload(const_cast<int*>(prm.tap_idx), idx) || upload(const_cast<T*>(prm.tap_w), w) ||
+            upload(const_cast<T*>(prm.basis), dense))
+            return -1;
+        basis_set = true;
+        return 0;
+    }
+    bool basis_dense = false, basis_set = false;
+    int basis_rows = 0;
+
+    int set_etd(const double* const tabs[6]) override {
+        if (cfg.equation != MPDE_KS) return fail("set_etdrk4: not a KS environment");
+        std::vector<T> h((size_t)6 * cfg.N);
+        for (int t = 0; t < 6; ++t)
+            for (int n = 0; n < cfg.N; ++n) h[(size_t)t * cfg.N + n] = (T)tabs[t][n];
+        etd_set = true;
+        return upload(const_cast<T*>(prm.etd), h);
+    }
+    bool etd_set = false;
+
+    int set_forcing(const double* coef, int64_t n) override {
+        if (!(cfg.flags & MPDE_FORCING)) return fail("set_forcing: environment was created without MPDE_FORCING");
+        if (n != 1 && n != cfg.nenvs) return fail("set_forcing: n must be 1 or nenvs");
+        std::vector<Cx<T>> h((size_t)n * cfg.stepper * 3);
+        for (size_t i = 0; i < h.size(); ++i) {
+            h[i].re = (T)coef[2 * i];
+            h[i].im = (T)coef[2 * i + 1];
+        }
+        n_forcing = (int)(n == 1 ? 1 : 2);
+        return upload(const_cast<Cx<T>*>(prm.fcoef), h);
+    }
+
+    int set_spectrum_ref(const double* ek, int64_t nref, int64_t rows, const int32_t* map) override {
+        (void)nref;
+        prm.ek_ref = ek;
+        prm.ek_rows = rows;
+        prm.ek_map = map;
+        return 0;
+    }
+    int set_truth(const void* truth, int64_t ntruth, int64_t rows, const int32_t* map) override {
+        (void)ntruth;
+        prm.truth = static_cast<const T*>(truth);
+        prm.truth_rows = rows;
+        prm.truth_map = map;
+        return 0;
+    }
+    int set_history(void* uu, void* vv, double* ektt, int64_t rows) override {
+        prm.uu_hist = static_cast<T*>(uu);
+        prm.vv_hist = static_cast<Cx<float>*>(vv);
+        prm.ektt_hist = ektt;
+        prm.hist_rows = (uu || vv || ektt) ? rows : 0;
+        return 0;
+    }
+
+    int reset(const void* src, bool spectral_ic, const uint8_t* mask, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (!src) return fail("reset: null initial condition");
+        int rc;
+        if (spectral()) {
+            rc = launch_spectral_aux<T>(prm, cfg.equation, spectral_ic ? AUX_RESET_V : AUX_RESET_U, src, mask, nullptr, st);
+        } else {
+            if (spectral_ic) return fail("reset_v: finite-difference environments take u0");
+            rc = launch_fd_reset<T>(prm, src, mask, st);
+        }
+        if (rc > 0) { launches += rc; rc = 0; }
+        if (rc < 0) return fail("reset: unsupported N for this equation (power of two, 4..4096)");
+        CU(cudaGetLastError());
+        return 0;
+    }
+
+    int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (nsub < 0) return fail("step: nsub < 0");
+        SpectralParams<T> p = prm;
+        p.nsub = nsub;
+        p.actions = static_cast<const T*>(actions);
+        p.state_out = static_cast<T*>(state_out);
+        p.reward_out = static_cast<T*>(reward_out);
+        p.reward_mode = cfg.reward_mode;
+        int flags = 0;
+        if (cfg.flags & MPDE_DFORCE) flags |= F_DFORCE;
+        if (cfg.flags & MPDE_FORCING) flags |= F_FORCING;
+        if (cfg.flags & MPDE_SSM) flags |= F_SSM;
+        if (cfg.flags & MPDE_DSM) flags |= F_DSM;
+        if (actions) {
+            if (cfg.M <= 0) return fail("step: actions given but M == 0 (call setup_basis first)");
+            if (spectral() && !basis_set) return fail("step: actions given but no basis was set");
+            flags |= F_ACTIONS;
+            if (basis_dense) flags |= F_BASIS_DENSE;
+        }
+        if (cfg.flags & MPDE_FORCING) {
+            if (n_forcing == 0) return fail("step: forcing enabled but mpde_set_forcing was never called");
+            if (n_forcing == 2) flags |= F_FORCING_PER_ENV;
+        }
+        if (nsub == 0) flags |= F_NO_ADVANCE;
+        p.flags = flags;
+        if (reward_out && nsub > 0) {
+            if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
+            if (cfg.reward_mode == MPDE_REWARD_MSE && !p.truth && cfg.equation == MPDE_BURGERS)
+                return fail("step: MSE reward without mpde_set_truth");
+        }
+        int rc;
+        switch (cfg.equation) {
+            case MPDE_BURGERS: rc = launch_burgers<T>(p, st); break;
+            case MPDE_KS:
+                if (!etd_set) return fail("step: KS tables missing (mpde_set_etdrk4)");
+                rc = launch_ks<T>(p, st);
+                break;
+            default: rc = launch_fd<T>(p, cfg.equation, (cfg.flags & MPDE_IMPLICIT) != 0, st); break;
+        }
+        if (rc < 0) return fail("step: unsupported N for this equation");
+        launches += rc;
+        CU(cudaGetLastError());
+        return 0;
+    }
+
+    int get(int field, void* dst, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        const int64_t B = cfg.nenvs;
+        const int N = cfg.N, NH = N / 2 + 1;
+        auto copy = [&](const void* src, size_t bytes) -> int {
+            CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        };
+        switch (field) {
+            case MPDE_FIELD_U:
+                if (spectral()) {
+                    int rc = launch_spectral_aux<T>(prm, cfg.equation, AUX_GET_U, nullptr, nullptr, dst, st);
+                    if (rc < 0) return fail("get(U): unsupported N");
+                    launches += rc;
+                    CU(cudaGetLastError());
+                    return 0;
+                }
+                return copy(prm.uprev, sizeof(T) * B * N);      // FD solvers keep u in the uprev slot
+            case MPDE_FIELD_V:
+            case MPDE_FIELD_FN_OLD: {
+                if (!spectral()) return fail("get: field only exists for spectral solvers");
+                const Cx<T>* half = field == MPDE_FIELD_V ? prm.v : prm.fn;
+                const int64_t n = B * N;
+                unpack_half_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(half, static_cast<Cx<T>*>(dst), B, N);
+                launches += 1;
+                CU(cudaGetLastError());
+                return 0;
+            }
+            case MPDE_FIELD_U_PREV: return copy(prm.uprev, sizeof(T) * B * N);
+            case MPDE_FIELD_EK_SUM:
+                if (!spectral()) return fail("get: field only exists for spectral solvers");
+                return copy(prm.acc, sizeof(float) * B * NH);
+            case MPDE_FIELD_IOUTNUM: return copy(prm.iout, sizeof(int) * B);
+            case MPDE_FIELD_T: return copy(prm.tnow, sizeof(T) * B);
+            case MPDE_FIELD_KPREV: return copy(prm.kprev, sizeof(T) * B);
+            case MPDE_FIELD_STATUS: return copy(prm.status, sizeof(int) * B);
+            case MPDE_FIELD_K:
+                if (!spectral()) return fail("get: field only exists for spectral solvers");
+                return copy(prm.kwave, sizeof(T) * N);
+            case MPDE_FIELD_NU: return copy(prm.nu, sizeof(T) * B);
+        }
+        return fail("get: unknown field");
+    }
+
+    int set(int field, const void* src, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        const int64_t B = cfg.nenvs;
+        const int N = cfg.N, NH = N / 2 + 1;
+        auto copy = [&](void* dst, size_t bytes) -> int {
+            CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        };
+        switch (field) {
+            case MPDE_FIELD_V:
+            case MPDE_FIELD_FN_OLD: {
+                if (!spectral()) return fail("set: field only exists for spectral solvers");
+                Cx<T>* half = field == MPDE_FIELD_V ? prm.v : prm.fn;
+                const int64_t n = B * NH;
+                pack_half_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const Cx<T>*>(src), half, B, N);
+                launches += 1;
+                CU(cudaGetLastError());
+                return 0;
+            }
+            case MPDE_FIELD_U:
+                if (spectral()) return fail("set(U): spectral solvers derive u from v; use mpde_reset_u or set V");
+                return copy(prm.uprev, sizeof(T) * B * N);
+            case MPDE_FIELD_U_PREV: return copy(prm.uprev, sizeof(T) * B * N);
+            case MPDE_FIELD_EK_SUM: return copy(prm.acc, sizeof(float) * B * NH);
+            case MPDE_FIELD_IOUTNUM: return copy(prm.iout, sizeof(int) * B);
+            case MPDE_FIELD_T: return copy(prm.tnow, sizeof(T) * B);
+            case MPDE_FIELD_KPREV: return copy(prm.kprev, sizeof(T) * B);
+            case MPDE_FIELD_STATUS: return copy(prm.status, sizeof(int) * B);
+            case MPDE_FIELD_NU: return copy(const_cast<T*>(prm.nu), sizeof(T) * B);
+        }
+        return fail("set: field is read-only or unknown");
+    }
+};
+
+extern "C" {
+
+int mpde_create(const mpde_config* cfg, mpde_env** out) {
+    if (!cfg || !out) return fail("create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(mpde_config)) return fail("create: mpde_config size mismatch (ABI)");
+    if (cfg->nenvs <= 0) return fail("create: nenvs must be positive");
+    if (cfg->N < 4) return fail("create: N must be >= 4");
+    const bool spectral = cfg->equation == MPDE_BURGERS || cfg->equation == MPDE_KS;
+    if (spectral && !is_pow2(cfg->N)) return fail("create: spectral solvers need a power-of-two N");
+    if (spectral && cfg->N > 4096) return fail("create: N > 4096 not supported");
+    if (cfg->num_agents < 1 || cfg->N % cfg->num_agents) return fail("create: num_agents must divide N");
+    if (cfg->stepper < 1) return fail("create: stepper must be >= 1");
+    if ((cfg->flags & MPDE_SSM) && (cfg->flags & MPDE_DSM)) return fail("create: ssm and dsm are exclusive (Burger.py:50)");
+    if (cfg->version < 0 || cfg->version > 4) return fail("create: version must be 0..4");
+    if (!(cfg->L > 0) || !(cfg->dt > 0)) return fail("create: L and dt must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("create: no CUDA device -- marlpde_b200 has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("create: bad device ordinal");
+    mpde_env* e = nullptr;
+    if (cfg->dtype == MPDE_F64) e = new Env<double>();
+    else if (cfg->dtype == MPDE_F32) e = new Env<float>();
+    else return fail("create: unknown dtype");
+    e->cfg = *cfg;
+    if (e->init() != 0) {
+        delete e;
+        return -1;
+    }
+    *out = e;
+    return 0;
+}
+
+int mpde_destroy(mpde_env* env) {
+    delete env;
+    return 0;
+}
+
+int64_t mpde_state_size(const mpde_env* env) { return env ? env->state_size() : -1; }
+int mpde_set_nu(mpde_env* env, const double* nu, int64_t n) { return env && nu ? env->set_nu(nu, n) : fail("null argument"); }
+int mpde_set_basis(mpde_env* env, int32_t M, const double* b) { return env && b ? env->set_basis(M, b) : fail("null argument"); }
+int mpde_set_reward_mode(mpde_env* env, int32_t mode) {
+    if (!env) return fail("null argument");
+    if (mode < 0 || mode > 3) return fail("set_reward_mode: unknown mode");
+    env->cfg.reward_mode = mode;
+    return 0;
+}
+int mpde_set_etdrk4(mpde_env* env, const double* E, const double* E2, const double* Q, const double* f1,
+                    const double* f2, const double* f3) {
+    if (!env || !E || !E2 || !Q || !f1 || !f2 || !f3) return fail("null argument");
+    const double* tabs[6] = {E, E2, Q, f1, f2, f3};
+    return env->set_etd(tabs);
+}
+int mpde_set_forcing(mpde_env* env, const double* c, int64_t n) { return env && c ? env->set_forcing(c, n) : fail("null argument"); }
+int mpde_set_spectrum_ref(mpde_env* env, const double* ek, int64_t nref, int64_t rows, const int32_t* map) {
+    return env && ek ? env->set_spectrum_ref(ek, nref, rows, map) : fail("null argument");
+}
+int mpde_set_truth(mpde_env* env, const void* t, int64_t nt, int64_t rows, const int32_t* map) {
+    return env && t ? env->set_truth(t, nt, rows, map) : fail("null argument");
+}
+int mpde_set_history(mpde_env* env, void* uu, void* vv, double* ektt, int64_t rows) {
+    return env ? env->set_history(uu, vv, ektt, rows) : fail("null argument");
+}
+int mpde_reset_u(mpde_env* env, const void* u0, const uint8_t* mask, void* stream) {
+    return env ? env->reset(u0, false, mask, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_reset_v(mpde_env* env, const void* v0, const uint8_t* mask, void* stream) {
+    return env ? env->reset(v0, true, mask, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
+    return env ? env->step(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
+    return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_set(mpde_env* env, int32_t field, const void* src, void* stream) {
+    return env && src ? env->set(field, src, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int64_t mpde_launch_count(const mpde_env* env) { return env ? env->launches : -1; }
+const char* mpde_last_error(void) { return g_err.c_str(); }
+int mpde_abi_version(void) { return MPDE_ABI_VERSION; }
+
+}  // extern "C"

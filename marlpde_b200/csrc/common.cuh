@@ -1,0 +1,53 @@
+// Shared device helpers for the marlpde_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cfloat>
+
+namespace mpde {
+
+template <typename T> struct Cx { T re, im; };
+
+template <typename T> __device__ __forceinline__ Cx<T> cx(T re, T im) { Cx<T> r; r.re = re; r.im = im; return r; }
+template <typename T> __device__ __forceinline__ Cx<T> operator+(Cx<T> a, Cx<T> b) { return cx<T>(a.re + b.re, a.im + b.im); }
+template <typename T> __device__ __forceinline__ Cx<T> operator-(Cx<T> a, Cx<T> b) { return cx<T>(a.re - b.re, a.im - b.im); }
+template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+    return cx<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+// a * conj(b)
+template <typename T> __device__ __forceinline__ Cx<T> cmulc(Cx<T> a, Cx<T> b) {
+    return cx<T>(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im);
+}
+template <typename T> __device__ __forceinline__ Cx<T> conj(Cx<T> a) { return cx<T>(a.re, -a.im); }
+
+// vector type with the same layout as Cx<T> for 8/16-byte global accesses
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename T> __device__ __forceinline__ Cx<T> ldcx(const Cx<T>* p) {
+    typename Vec2<T>::type v = *reinterpret_cast<const typename Vec2<T>::type*>(p);
+    return cx<T>(v.x, v.y);
+}
+template <typename T> __device__ __forceinline__ void stcx(Cx<T>* p, Cx<T> a) {
+    typename Vec2<T>::type v; v.x = a.re; v.y = a.im;
+    *reinterpret_cast<typename Vec2<T>::type*>(p) = v;
+}
+
+__device__ __forceinline__ double shfl(double v, int src, unsigned mask = 0xffffffffu) { return __shfl_sync(mask, v, src); }
+__device__ __forceinline__ float shfl(float v, int src, unsigned mask = 0xffffffffu) { return __shfl_sync(mask, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename T> __device__ __forceinline__ Cx<T> shfl_xor(Cx<T> v, int m) { return cx<T>(shfl_xor(v.re, m), shfl_xor(v.im, m)); }
+template <typename T> __device__ __forceinline__ Cx<T> shfl(Cx<T> v, int src) { return cx<T>(shfl(v.re, src), shfl(v.im, src)); }
+
+// The reference traps overflow when it casts v to complex64 for its history
+// (Burger.py:8,498 / KS.py:7,273): an env is "blown up" as soon as a component of v
+// is not representable in float32 (this also catches NaN/inf).
+template <typename T> __device__ __forceinline__ bool blown(Cx<T> v) {
+    return !(fabs((double)v.re) <= (double)FLT_MAX && fabs((double)v.im) <= (double)FLT_MAX);
+}
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+}  // namespace mpde

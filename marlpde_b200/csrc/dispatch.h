@@ -1,0 +1,39 @@
+// Kernel launchers (one translation unit per solver family keeps nvcc times short).
+// Each returns the number of kernels it launched, or -1 when N is not supported.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdlib>
+#include "params.h"
+#include "pack.cuh"
+
+namespace mpde {
+
+template <typename T> int launch_burgers(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_cta(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T>
+int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
+                            void* dst, cudaStream_t st);
+template <typename T> int launch_ks(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_fd(const SpectralParams<T>& p, int equation, bool implicit, cudaStream_t st);
+template <typename T> int launch_fd_reset(const SpectralParams<T>& p, const void* src, const uint8_t* mask, cudaStream_t st);
+template <typename T>
+int launch_spectral_aux(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
+                        void* dst, cudaStream_t st);
+
+// Grid geometry of the warp-resident kernels: a team of min(N,32) lanes per PAIR of
+// environments.  Small batches get one warp per CTA so the 148 SMs fill evenly; large
+// batches use 4-warp CTAs.  MPDE_WPC overrides (tuning).
+inline void warp_geometry(int64_t B, int N, int& grid, int& block) {
+    const int TS = N < 32 ? N : 32, TPW = 32 / TS;
+    const int64_t pairs = (B + 1) / 2;
+    const int64_t warps = (pairs + TPW - 1) / TPW;
+    int wpc = warps >= 148 * 32 ? 4 : (warps >= 148 * 8 ? 2 : 1);
+    if (const char* s = std::getenv("MPDE_WPC")) {
+        const int v = std::atoi(s);
+        if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
+    }
+    grid = (int)((warps + wpc - 1) / wpc);
+    block = 32 * wpc;
+}
+
+}  // namespace mpde
