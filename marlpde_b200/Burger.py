@@ -374,6 +374,7 @@ class Burger(BatchedEnv):
     def getState(self, nAgents=None, as_tensor=None):
         """Burger.py:604-675.  nenvs == 1: the reference's nested lists; else [B,S] / [B,A,S/A]."""
         if self._state_at != self.ioutnum:
+            self._upload_forcing()
             L_check(self._lib.mpde_step(self._h, None, 0, self._ptr(self._state_buf), None, self._stream()))
             self._state_at = self.ioutnum
         A = self.numAgents
@@ -389,6 +390,7 @@ class Burger(BatchedEnv):
         """Burger.py:578-601 -> rewards per agent; nenvs == 1: numpy [A]."""
         self._ensure_truth(shift)
         if self._reward_at != self.ioutnum:
+            self._upload_forcing()
             L_check(self._lib.mpde_step(self._h, None, 0, None, self._ptr(self._reward_buf), self._stream()))
             self._reward_at = self.ioutnum
         if as_tensor is None:

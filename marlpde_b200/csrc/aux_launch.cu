@@ -26,6 +26,7 @@ int launch_spectral_aux(const SpectralParams<T>& p, int equation, int mode, cons
         case 32: return launch_aux_warp<T, 32>(p, equation, mode, src, mask, dst, st);
         case 64: return launch_aux_warp<T, 64>(p, equation, mode, src, mask, dst, st);
         case 128: return launch_aux_warp<T, 128>(p, equation, mode, src, mask, dst, st);
+        case 256: return launch_aux_warp<T, 256>(p, equation, mode, src, mask, dst, st);
         default: return launch_spectral_aux_cta<T>(p, equation, mode, src, mask, dst, st);
     }
 }

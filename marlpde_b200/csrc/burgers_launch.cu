@@ -14,9 +14,7 @@ template <typename T, int N>
 static int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
     int grid, block;
     warp_geometry(p.B, N, grid, block);
-    const int TS = N < 32 ? N : 32, TPW = 32 / TS;
-    const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
-    const size_t smem = (size_t)(block / 32) * TPW * 2 * scr * sizeof(T);
+    const size_t smem = warp_scratch_bytes(N, p.M, block, sizeof(T));
     burgers_warp_kernel<T, N><<<grid, block, smem, st>>>(p);
     return 1;
 }
@@ -29,6 +27,7 @@ int launch_burgers(const SpectralParams<T>& p, cudaStream_t st) {
         case 32: return launch_warp<T, 32>(p, st);
         case 64: return launch_warp<T, 64>(p, st);
         case 128: return launch_warp<T, 128>(p, st);
+        case 256: return launch_warp<T, 256>(p, st);
         default: return launch_burgers_cta<T>(p, st);
     }
 }

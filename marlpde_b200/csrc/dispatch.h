@@ -20,20 +20,24 @@ template <typename T>
 int launch_spectral_aux(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
                         void* dst, cudaStream_t st);
 
-// Grid geometry of the warp-resident kernels: a team of min(N,32) lanes per PAIR of
-// environments.  Small batches get one warp per CTA so the 148 SMs fill evenly; large
-// batches use 4-warp CTAs.  MPDE_WPC overrides (tuning).
+// Grid geometry of the warp-resident kernels: a team of min(N/2, 32) lanes per environment.
+// Small batches get one warp per CTA so the 148 SMs fill evenly; large batches use 4-warp
+// CTAs.  MPDE_WPC overrides (tuning).
 inline void warp_geometry(int64_t B, int N, int& grid, int& block) {
-    const int TS = N < 32 ? N : 32, TPW = 32 / TS;
-    const int64_t pairs = (B + 1) / 2;
-    const int64_t warps = (pairs + TPW - 1) / TPW;
+    const int H = N / 2, TS = H < 32 ? H : 32, TPW = 32 / TS;
+    const int64_t warps = (B + TPW - 1) / TPW;
     int wpc = warps >= 148 * 32 ? 4 : (warps >= 148 * 8 ? 2 : 1);
     if (const char* s = std::getenv("MPDE_WPC")) {
         const int v = std::atoi(s);
-        if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
+        if (v == 1 || v == 2 || v == 4) wpc = v;
     }
     grid = (int)((warps + wpc - 1) / wpc);
     block = 32 * wpc;
+}
+inline size_t warp_scratch_bytes(int N, int M, int block, size_t elem) {
+    const int H = N / 2, TS = H < 32 ? H : 32, TPW = 32 / TS;
+    const int scr = M > 2 * N + N / 2 ? M : 2 * N + N / 2;
+    return (size_t)(block / 32) * TPW * scr * elem;
 }
 
 }  // namespace mpde

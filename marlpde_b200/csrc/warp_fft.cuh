@@ -1,15 +1,19 @@
-// Warp-level radix-2 FFT on register-resident data, for N <= 128 (sm_100a).
+// Warp-level FFTs on register-resident data (sm_100a).
 //
-// A "team" of TS = min(N, 32) lanes owns one length-N complex sequence; lane tl holds
-// the P = N/TS points n = p*TS + tl.  Forward = decimation-in-frequency (natural order
-// in, BIT-REVERSED order out): the first log2(P) stages pair registers of one lane, the
-// last log2(TS) stages pair lanes through __shfl_xor.  Inverse = the exact transpose
-// (decimation-in-time, bit-reversed in, natural out, unnormalised).  Spectral
-// arithmetic is done in the bit-reversed layout, so no permutation pass is ever needed.
+// WarpFFT<T, H>: radix-2 complex FFT of H <= 128 points.  A "team" of TS = min(H, 32)
+// lanes owns one sequence; lane tl holds the P = H/TS points j = p*TS + tl.  Forward =
+// decimation-in-frequency (natural order in, BIT-REVERSED order out): the first log2(P)
+// stages pair registers of one lane, the last log2(TS) stages pair lanes through
+// __shfl_xor.  Inverse = the exact transpose (decimation-in-time, bit-reversed in, natural
+// out, unnormalised).  Spectral arithmetic is done in the bit-reversed layout, so no
+// permutation pass is ever needed.
 //
-// One complex transform carries TWO real fields (environment A in the real part,
-// environment B in the imaginary part): untangle() splits the two Hermitian spectra,
-// tangle() packs two Hermitian spectra for a single inverse transform.
+// RealFFT<T, N>: transform of ONE real length-N field per team through a complex FFT of
+// H = N/2 points on z_j = x_{2j} + i x_{2j+1} plus the usual split/merge step.  The team
+// then holds exactly the half spectrum X_0..X_{H-1} (one wavenumber per register, bit-
+// reversed order) and the real Nyquist value X_H on its first lane.  Every environment's
+// arithmetic is independent of its neighbours in the warp, which is what makes results
+// bitwise invariant to batch size and packing.
 #pragma once
 #include "common.cuh"
 
@@ -21,51 +25,52 @@ __host__ __device__ constexpr int brev_bits(int x, int bits) {
     return r;
 }
 
-template <typename T, int N>
+// TWS: stride into the twiddle table (table holds exp(-2 pi i j / (H*TWS)))
+template <typename T, int H, int TWS = 1>
 struct WarpFFT {
-    static constexpr int TS = N < 32 ? N : 32;
-    static constexpr int P = N / TS;
-    static constexpr int LOGN = ilog2(N);
+    static constexpr int TS = H < 32 ? H : 32;
+    static constexpr int P = H / TS;
+    static constexpr int LOGH = ilog2(H);
     static constexpr int LOGTS = ilog2(TS);
     static constexpr int LOGP = ilog2(P);
-    static_assert((1 << LOGN) == N && N >= 4 && N <= 128, "warp FFT handles N = 4..128, power of two");
+    static_assert((1 << LOGH) == H && H >= 2 && H <= 128, "warp FFT handles 2..128 points, power of two");
 
     int tl;                         // lane within the team
     int base;                       // first lane of the team within the warp
-    Cx<T> wx[LOGTS];                // cross-lane twiddles, (1,0) on the lower lane of a pair
+    Cx<T> wx[LOGTS > 0 ? LOGTS : 1];  // cross-lane twiddles, (1,0) on the lower lane of a pair
     Cx<T> wl[P > 1 ? P - 1 : 1];    // in-register twiddles
-    int part[P];                    // lane holding wavenumber -k for register pp(p)
+    int part[P];                    // lane holding wavenumber -k (mod H) for register pp(p)
 
     // register index that holds -k for the k held in register p (depends on p only)
     __host__ __device__ static constexpr int pp(int p) {
         return brev_bits((P - brev_bits(p, LOGP)) % P, LOGP);
     }
-    // wavenumber index (0..N-1, FFT order) held at register p of team-lane t after fwd()
+    // wavenumber index (0..H-1) held at register p of team-lane t after fwd()
     __device__ __forceinline__ static int kidx(int p, int t) {
-        return (int)(__brev((unsigned)(p * TS + t)) >> (32 - LOGN));
+        return (int)(__brev((unsigned)(p * TS + t)) >> (32 - LOGH));
     }
 
-    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw /* [N/2]: exp(-2 pi i j/N) */) {
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw) {
         const int lane = threadIdx.x & 31;
         tl = lane & (TS - 1);
         base = lane & ~(TS - 1);
 #pragma unroll
         for (int s = 0; s < LOGTS; ++s) {
             const int h = TS >> (s + 1);
-            wx[s] = (tl & h) ? ldcx(tw + (tl & (h - 1)) * (N / (2 * h))) : cx<T>(T(1), T(0));
+            wx[s] = (tl & h) ? ldcx(tw + (tl & (h - 1)) * (H / (2 * h)) * TWS) : cx<T>(T(1), T(0));
         }
         if constexpr (P > 1) {
 #pragma unroll
             for (int hp = P / 2; hp >= 1; hp >>= 1)
 #pragma unroll
                 for (int q = 0; q < hp; ++q)
-                    wl[P - 2 * hp + q] = ldcx(tw + (q * TS + tl) * (P / (2 * hp)));
+                    wl[P - 2 * hp + q] = ldcx(tw + (q * TS + tl) * (P / (2 * hp)) * TWS);
         }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const int k = kidx(p, tl);
-            const int kneg = (N - k) & (N - 1);
-            const int npos = (int)(__brev((unsigned)kneg) >> (32 - LOGN));   // position holding -k
+            const int kneg = (H - k) & (H - 1);
+            const int npos = (int)(__brev((unsigned)kneg) >> (32 - LOGH));   // position holding -k
             part[p] = base + (npos & (TS - 1));
         }
     }
@@ -96,7 +101,7 @@ struct WarpFFT {
         }
     }
 
-    // bit-reversed spectrum -> natural order, unnormalised inverse DFT (N * ifft)
+    // bit-reversed spectrum -> natural order, unnormalised inverse DFT (H * ifft)
     __device__ __forceinline__ void inv(Cx<T> (&z)[P]) const {
 #pragma unroll
         for (int s = LOGTS - 1; s >= 0; --s) {
@@ -123,22 +128,60 @@ struct WarpFFT {
         }
     }
 
-    // Z = fwd(xA + i xB)  ->  XA = fft(xA), XB = fft(xB) at this lane's wavenumbers,
-    // both multiplied by `scale`
-    __device__ __forceinline__ void untangle(const Cx<T> (&z)[P], Cx<T> (&xa)[P], Cx<T> (&xb)[P], T scale) const {
+    // value held for wavenumber -k (mod H) by the team, for the k of register p
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[P], int p) const { return shfl(z[pp(p)], part[p]); }
+};
+
+template <typename T, int N>
+struct RealFFT {
+    static constexpr int H = N / 2;
+    using C = WarpFFT<T, H, 2>;
+    static constexpr int TS = C::TS, P = C::P;
+    static_assert(N >= 8 && N <= 256, "warp-resident real FFT handles N = 8..256");
+
+    C c;
+    Cx<T> wk[P];     // exp(-2 pi i k / N) for the wavenumber k of register p
+    bool dc;         // this lane's register 0 holds k = 0 (and owns the Nyquist value)
+
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw /* [N/2]: exp(-2 pi i j / N) */) {
+        c.init(tw);
+#pragma unroll
+        for (int p = 0; p < P; ++p) wk[p] = ldcx(tw + C::kidx(p, c.tl));
+        dc = c.tl == 0;
+    }
+    // wavenumber index 0..H-1 of register p
+    __device__ __forceinline__ int k(int p) const { return C::kidx(p, c.tl); }
+
+    // z[p] = (x_{2j}, x_{2j+1}), j = p*TS + tl   ->   X[p] = scale * fft(x)[k(p)],
+    // nyq = scale * fft(x)[N/2] (real; meaningful on the dc lane only).  z is clobbered.
+    __device__ __forceinline__ void fwd(Cx<T> (&z)[P], Cx<T> (&X)[P], T& nyq, T scale) const {
+        c.fwd(z);
         const T hs = T(0.5) * scale;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            const Cx<T> zp = shfl(z[pp(p)], part[p]);                  // Z[-k]
-            xa[p] = cx<T>((z[p].re + zp.re) * hs, (z[p].im - zp.im) * hs);
-            xb[p] = cx<T>((z[p].im + zp.im) * hs, (zp.re - z[p].re) * hs);
+            const Cx<T> zp = c.mirrored(z, p);                                   // Z[H-k]
+            const Cx<T> E = cx<T>(z[p].re + zp.re, z[p].im - zp.im);            // 2 * fft(x_even)[k]
+            const Cx<T> O = cx<T>(z[p].im + zp.im, zp.re - z[p].re);            // 2 * fft(x_odd)[k]
+            const Cx<T> wO = cmul(wk[p], O);
+            X[p] = cx<T>((E.re + wO.re) * hs, (E.im + wO.im) * hs);
+            if (p == 0) nyq = (E.re - O.re) * hs;                                // k = 0: E, O real
         }
     }
-
-    // Z = SA + i SB for two Hermitian spectra.  `selfc[p]` marks k = 0 and k = N/2, where
-    // only the real part of a spectrum reaches Re(ifft) (Burger.py:491 takes np.real).
-    __device__ __forceinline__ static Cx<T> tangle(Cx<T> sa, Cx<T> sb, bool selfc) {
-        return selfc ? cx<T>(sa.re, sb.re) : cx<T>(sa.re - sb.im, sa.im + sb.re);
+    // X[p] = spectrum at k(p), nyq = real Nyquist value (dc lane)  ->  z[p] = scale * N * ifft(X)
+    // at points (2j, 2j+1).  Only the real parts of X_0 and X_{N/2} enter (np.real(ifft(.))).
+    __device__ __forceinline__ void inv(const Cx<T> (&X)[P], T nyq, Cx<T> (&z)[P], T scale) const {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const Cx<T> xp = c.mirrored(X, p);                                   // X[H-k]
+            const Cx<T> E = cx<T>(X[p].re + xp.re, X[p].im - xp.im);
+            const Cx<T> D = cx<T>(X[p].re - xp.re, X[p].im + xp.im);
+            const Cx<T> O = cmulc(D, wk[p]);
+            z[p] = cx<T>(E.re - O.im, E.im + O.re);
+            if (p == 0 && dc) z[p] = cx<T>(X[p].re + nyq, X[p].re - nyq);
+        }
+        c.inv(z);
+#pragma unroll
+        for (int p = 0; p < P; ++p) { z[p].re *= scale; z[p].im *= scale; }
     }
 };
 
