@@ -1,0 +1,304 @@
+#!/usr/bin/env python3
+"""Benchmark of the marlpde environment time-stepper hot path (BASELINE.json metric:
+env-steps/s, batched Burgers LES N=32 x 4096 envs per GPU, fp64, stochastic forcing,
+spectral reward, nIntermediate = 10 solver steps per RL step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA)
+  python bench.py --impl reference ...                             # CPU reference arm (numpy port)
+
+One "step" = one RL step of the whole batch = ONE kernel launch: 10 ABCN solver steps with
+the actions held fixed + getState + spectral reward (burger_environment.py:148-176).
+Prints ONE JSON line (see the driver contract in the task description).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ----------------------------------------------------------------------------- workload
+B_PER_GPU = 4096           # BASELINE.json configs[1]
+N, M, NSUB = 32, 32, 10
+L_DOM, DT, NU, TEND = 2 * np.pi, 1e-3, 0.02, 5.0
+POOL = 24                  # independent batches rotated so the working set exceeds L2
+# algorithmic bytes one launch must move per environment (DESIGN.md "Roofline"):
+#   read  actions M*8 + v,Fn_old 2*(N/2+1)*16 + Ek sums (N/2+1)*4 + counters 28 + forcing 48
+#   write v,Fn_old 2*(N/2+1)*16 + Ek sums + u_prev N*8 + state N*8 + reward 8 + counters 12
+BYTES_PER_ENV_LAUNCH = (M * 8 + 2 * 17 * 16 + 17 * 4 + 28 + 48) + (2 * 17 * 16 + 17 * 4 + N * 8 + N * 8 + 8 + 12)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One process = one reference-style environment stepped one solver step per Python call
+    (the reference has no batching: burger_environment.py:134-192)."""
+    seed, seconds, rl_steps = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle.burger_oracle import BurgerOracle, forcing_tables, turbulence_ic
+    from oracle.common import grid, spectral_rel_err
+    rng = np.random.default_rng(seed)
+    o = BurgerOracle(B=1, L=L_DOM, N=N, dt=DT, nu=NU, forcing=True, dforce=False)
+    o.setup_basis(M, "hat")
+    r1, r2 = forcing_tables(42 + seed % 7, 8)
+    o.set_forcing_tables(r1, r2)
+    o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, 42 + seed % 7)[None])
+    ref = np.abs(rng.normal(1.0, 0.1, (5001, N // 2))) * 1e-3 + 1e-6
+    acts = rng.uniform(0.0, 0.02, (1, M))
+    prev, done, t0 = 0.0, 0, time.perf_counter()
+    while True:
+        for _ in range(NSUB):
+            o.step(acts)
+        o.state()
+        err = spectral_rel_err(ref[min(o.ioutnum, 5000)], o.Ek_ktt_row()[0], N)
+        prev = err
+        done += 1
+        if o.ioutnum >= 4000:
+            o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, 42 + seed % 7)[None])
+        if (rl_steps and done >= rl_steps) or (not rl_steps and time.perf_counter() - t0 >= seconds):
+            break
+    return done * NSUB, time.perf_counter() - t0
+
+
+def cpu_run(seconds=None, rl_steps=None, cores=None):
+    cores = cores or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(i, seconds, rl_steps) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return steps / busy, cores, steps, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: every step = `cores` environments x 1 RL step (10 solver steps), all host cores busy
+    cores = len(os.sched_getaffinity(0))
+    total_rl = args.steps + args.warmup
+    per_proc = max(1, min(total_rl, 400))
+    value, cores, steps, wall = cpu_run(rl_steps=per_proc, cores=cores)
+    sample = (f"{cores} single-env numpy-port processes (one per host core) x {per_proc} RL steps x {NSUB} solver steps, "
+              "Burgers N=32 forcing+eddy action+spectral reward, one step() per Python call as in the reference")
+    line = {
+        "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores * NSUB / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
+                        f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
+                        f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of the batch",
+            "envs_per_gpu": B_PER_GPU, "N": N, "M": M, "n_intermediate": NSUB, "global_envs": B_PER_GPU * n_gpus,
+            "l2": f"rotating pool of {POOL} independent batches per GPU (state working set > 126 MB L2)",
+            "parallelism": f"env-sharded x{n_gpus}, all_gather of state+reward per RL step" if n_gpus > 1 else "single GPU"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def make_batch(torch, device, seed0):
+    from marlpde_b200 import Burger
+    seeds = seed0 + (np.arange(B_PER_GPU) % 16)
+    env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=True, dforce=False, seed=seeds,
+                 nenvs=B_PER_GPU, device=device, history=False)
+    env.setup_basis(M, "hat")
+    rng = np.random.default_rng(seed0)
+    env.set_spectrum_reference(np.abs(rng.normal(1.0, 0.1, (int(TEND / DT) + 1, N // 2))) * 1e-3 + 1e-6)
+    return env
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    K, W = args.steps, args.warmup
+    pool = max(1, args.pool)
+    envs = [make_batch(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
+    rng = np.random.default_rng(rank)
+    acts_host = torch.from_numpy(rng.uniform(0.0, 0.02, (pool, B_PER_GPU, M))).pin_memory()
+    acts = acts_host.to(device)
+    S = envs[0]._state_size
+    if world > 1:
+        g_state = torch.empty((world * B_PER_GPU, S), device=device, dtype=torch.float64)
+        g_reward = torch.empty((world * B_PER_GPU, 1), device=device, dtype=torch.float64)
+
+    def one_step(i):
+        env = envs[i % pool]
+        st, rw = env.step_n(acts[i % pool], NSUB)
+        if world > 1:      # learner-side gather of per-env summaries (north_star: the only collective)
+            dist.all_gather_into_tensor(g_state, st)
+            dist.all_gather_into_tensor(g_reward, rw)
+        return st, rw
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = sum(e.launch_count for e in envs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        one_step(W + i)
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(e.launch_count for e in envs) - l0
+    clocks = sampler.stop() if sampler else None
+    alive = all(int((e.status != 0).sum()) == 0 for e in envs)
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    st_host = torch.empty((B_PER_GPU, S), dtype=torch.float64).pin_memory()
+    rw_host = torch.empty((B_PER_GPU, 1), dtype=torch.float64).pin_memory()
+    a_dev = torch.empty((B_PER_GPU, M), device=device, dtype=torch.float64)
+    Ke = max(10, min(K, 200))
+
+    def e2e_step(i):
+        env = envs[i % pool]
+        a_dev.copy_(acts_host[i % pool], non_blocking=True)               # H2D of this step's actions
+        st, rw = env.step_n(a_dev, NSUB)
+        if world > 1:
+            dist.all_gather_into_tensor(g_state, st)
+            dist.all_gather_into_tensor(g_reward, rw)
+        st_host.copy_(st, non_blocking=True)                              # D2H of state + reward
+        rw_host.copy_(rw, non_blocking=True)
+        torch.cuda.synchronize()                                          # the learner needs them before acting
+
+    for i in range(3):
+        e2e_step(i)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(3 + i)
+    sync()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+        ok = torch.tensor([1 if alive else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        alive = bool(ok.item())
+
+    if rank == 0:
+        total_envs = B_PER_GPU * world
+        value = total_envs * NSUB * K / (ms * 1e-3)
+        peak, how = peaks()
+        per_launch_s = ms * 1e-3 / K
+        achieved = B_PER_GPU * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
+        line = {
+            "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
+                    "h2d_bytes_per_step": B_PER_GPU * M * 8, "d2h_bytes_per_step": B_PER_GPU * (S + 1) * 8,
+                    "steps": Ke, "note": "pinned host actions -> H2D -> step_n -> D2H state+reward -> sync, per RL step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": how, "kernel": "burgers_warp_kernel<double,32>",
+                         "bytes_per_launch": B_PER_GPU * BYTES_PER_ENV_LAUNCH,
+                         "note": "launch-latency bound at B=4096 (7.6 MB per launch); 10 fused sub-steps per launch "
+                                 "make the kernel FP64/shuffle bound, see DESIGN.md and profiles/"},
+            "all_envs_alive": alive,
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, steps, wall = cpu_run(seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cores} single-env numpy-port processes x {args.cpu_seconds:.0f} s of the same "
+                                              f"workload (N=32, forcing, eddy action, spectral reward, one step() per call)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
