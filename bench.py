@@ -29,6 +29,7 @@ B_PER_GPU = 4096           # BASELINE.json configs[1]
 N, M, NSUB = 32, 32, 10
 L_DOM, DT, NU, TEND = 2 * np.pi, 1e-3, 0.02, 5.0
 POOL = 24                  # independent batches rotated so the working set exceeds L2
+STABLE_SEEDS = (50, 59, 81, 89)
 # algorithmic bytes one launch must move per environment (DESIGN.md "Roofline"):
 #   read  actions M*8 + v,Fn_old 2*(N/2+1)*16 + Ek sums (N/2+1)*4 + counters 28 + forcing 48
 #   write v,Fn_old 2*(N/2+1)*16 + Ek sums + u_prev N*8 + state N*8 + reward 8 + counters 12
@@ -52,7 +53,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -92,11 +93,12 @@ def _cpu_worker(args):
     rng = np.random.default_rng(seed)
     o = BurgerOracle(B=1, L=L_DOM, N=N, dt=DT, nu=NU, forcing=True, dforce=False)
     o.setup_basis(M, "hat")
-    r1, r2 = forcing_tables(42 + seed % 7, 8)
-    o.set_forcing_tables(r1, r2)
-    o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, 42 + seed % 7)[None])
+    sd = STABLE_SEEDS[seed % len(STABLE_SEEDS)]
+    r1, r2 = forcing_tables(sd, int(TEND / DT))
+    o.set_forcing_tables(r1[:, :1], r2[:, :1])
+    o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, sd)[None])
     ref = np.abs(rng.normal(1.0, 0.1, (5001, N // 2))) * 1e-3 + 1e-6
-    acts = rng.uniform(0.0, 0.02, (1, M))
+    acts = np.full((1, M), rng.uniform(0.05, 0.1))
     prev, done, t0 = 0.0, 0, time.perf_counter()
     while True:
         for _ in range(NSUB):
@@ -106,7 +108,7 @@ def _cpu_worker(args):
         prev = err
         done += 1
         if o.ioutnum >= 4000:
-            o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, 42 + seed % 7)[None])
+            o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, sd)[None])
         if (rl_steps and done >= rl_steps) or (not rl_steps and time.perf_counter() - t0 >= seconds):
             break
     return done * NSUB, time.perf_counter() - t0
@@ -159,7 +161,10 @@ def workload_config(n_gpus):
 # ----------------------------------------------------------------------------- GPU arm
 def make_batch(torch, device, seed0):
     from marlpde_b200 import Burger
-    seeds = seed0 + (np.arange(B_PER_GPU) % 16)
+    # forced N=32 LES blows up for most forcing seeds within ~10^3 steps (the reference's own physics);
+    # these four stay bounded for a whole episode under a positive eddy viscosity, so every
+    # environment stays alive (= does all its arithmetic) during the timed region
+    seeds = np.array(STABLE_SEEDS)[(np.arange(B_PER_GPU) + seed0) % len(STABLE_SEEDS)]
     env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=True, dforce=False, seed=seeds,
                  nenvs=B_PER_GPU, device=device, history=False)
     env.setup_basis(M, "hat")
@@ -182,7 +187,8 @@ def gpu_arm(args):
     pool = max(1, args.pool)
     envs = [make_batch(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
     rng = np.random.default_rng(rank)
-    acts_host = torch.from_numpy(rng.uniform(0.0, 0.02, (pool, B_PER_GPU, M))).pin_memory()
+    # one eddy-viscosity coefficient per environment, replicated over its M actions
+    acts_host = torch.from_numpy(np.repeat(rng.uniform(0.05, 0.1, (pool, B_PER_GPU, 1)), M, axis=2).copy()).pin_memory()
     acts = acts_host.to(device)
     S = envs[0]._state_size
     if world > 1:
@@ -202,10 +208,10 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None      # covers warm-up + timed + e2e regions
     for i in range(W):
         one_step(i)
     sync()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = sum(e.launch_count for e in envs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -215,14 +221,13 @@ def gpu_arm(args):
     sync()
     ms = ev0.elapsed_time(ev1)
     launches = sum(e.launch_count for e in envs) - l0
-    clocks = sampler.stop() if sampler else None
     alive = all(int((e.status != 0).sum()) == 0 for e in envs)
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     st_host = torch.empty((B_PER_GPU, S), dtype=torch.float64).pin_memory()
     rw_host = torch.empty((B_PER_GPU, 1), dtype=torch.float64).pin_memory()
     a_dev = torch.empty((B_PER_GPU, M), device=device, dtype=torch.float64)
-    Ke = max(10, min(K, 200))
+    Ke = max(10, min(K, 1000))
 
     def e2e_step(i):
         env = envs[i % pool]
@@ -243,6 +248,7 @@ def gpu_arm(args):
         e2e_step(3 + i)
     sync()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3], device=device, dtype=torch.float64)
@@ -287,8 +293,8 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

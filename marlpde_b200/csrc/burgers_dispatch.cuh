@@ -1,0 +1,65 @@
+// Shared launcher template of the warp-resident Burgers kernels.
+#pragma once
+#include "dispatch.h"
+#include "burgers_warp.cuh"
+
+namespace mpde {
+
+// register budget: one wave of warps must fit for the small-batch (latency) regime
+template <typename T, int N, int TS>
+constexpr int min_blocks() {
+    constexpr int P = N / 2 / TS;
+    return (sizeof(T) == 8 ? (P <= 1 ? 8 : (P <= 2 ? 6 : 4)) : (P <= 2 ? 8 : 4));
+}
+
+template <typename T, int N, int TS, int SF>
+__global__ void __launch_bounds__(64, (min_blocks<T, N, TS>())) burgers_warp_kernel(const SpectralParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BurgersWarp<T, N, TS, SF>::run(prm, reinterpret_cast<T*>(smem_raw));
+}
+
+template <typename T, int N, int TS, int SF>
+int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
+    constexpr int TPW = 32 / TS;
+    const int64_t warps = (p.B + TPW - 1) / TPW;
+    const int block = 64;
+    const int grid = (int)((warps + 1) / 2);
+    const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
+    const size_t smem = (size_t)2 * TPW * scr * sizeof(T);
+    burgers_warp_kernel<T, N, TS, SF><<<grid, block, smem, st>>>(p);
+    return 1;
+}
+
+// structural-flag specialisations compiled for the hot grid sizes
+template <typename T, int N, int TS>
+int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
+    if constexpr (sizeof(T) == 8) {
+        switch (p.flags & STRUCT_FLAGS) {
+            case F_ACTIONS: return launch_warp<T, N, TS, F_ACTIONS>(p, st);
+            case F_ACTIONS | F_FORCING: return launch_warp<T, N, TS, F_ACTIONS | F_FORCING>(p, st);
+            case F_ACTIONS | F_DFORCE: return launch_warp<T, N, TS, F_ACTIONS | F_DFORCE>(p, st);
+            case F_ACTIONS | F_DFORCE | F_FORCING: return launch_warp<T, N, TS, F_ACTIONS | F_DFORCE | F_FORCING>(p, st);
+            case 0:
+            case F_DFORCE: return launch_warp<T, N, TS, 0>(p, st);
+            case F_FORCING:
+            case F_FORCING | F_DFORCE: return launch_warp<T, N, TS, F_FORCING>(p, st);
+            default: break;
+        }
+    }
+    return launch_warp<T, N, TS, -1>(p, st);
+}
+
+// Team size: the widest team (lowest latency) unless the batch is large enough to keep every
+// SM sub-partition busy with narrower teams (fewer instructions per environment).
+// MPDE_TS overrides (tuning).
+inline int pick_team(int64_t B, int N, int ts_max, int ts_min) {
+    if (const char* s = std::getenv("MPDE_TS")) {
+        const int v = std::atoi(s);
+        if (v >= ts_min && v <= ts_max && (v & (v - 1)) == 0) return v;
+    }
+    int ts = ts_max;
+    while (ts > ts_min && (B * (ts / 2) / 32) >= (int64_t)148 * 4 * MPDE_WARPS_PER_SMSP_TARGET) ts /= 2;
+    return ts;
+}
+
+}  // namespace mpde

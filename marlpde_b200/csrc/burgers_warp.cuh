@@ -3,13 +3,16 @@
 // Restates the arithmetic of the reference Burger.step() + getState() + rewards
 // (/root/reference/python/_model/Burger.py:333-499, 541-576, 578-675 and
 // burger_environment.py:148-176) for a batch of independent environments:
-//   * one team of min(N/2, 32) lanes owns one environment (N = 32: two environments per
-//     warp); lane registers hold the half spectrum of v and Fn_old, one or a few
-//     wavenumbers each, plus two adjacent grid points of u;
+//   * a team of TS lanes owns one environment (32/TS environments per warp); lane
+//     registers hold P = N/(2 TS) wavenumbers of the half spectra of v and Fn_old plus 2P
+//     adjacent grid points of u.  TS is a template parameter: wide teams minimise latency
+//     for small batches, narrow teams minimise instructions per environment for large ones;
 //   * the state is read once, `nsub` ABCN sub-steps run out of registers on a shuffle
 //     real-FFT, then state / reward / spectrum sums are written back coalesced;
 //   * action forcing, 3-mode stochastic forcing, Smagorinsky closures, the float32
-//     spectrum chain and the spectral / MSE rewards are fused in.
+//     spectrum chain and the spectral / MSE rewards are fused in;
+//   * SF >= 0 fixes the structural mode flags at compile time (hot configurations), SF < 0
+//     reads them at run time (generic kernel).
 // No arithmetic of one environment depends on another one: results are bitwise
 // independent of batch size and packing.
 #pragma once
@@ -18,25 +21,27 @@
 
 namespace mpde {
 
+constexpr int STRUCT_FLAGS = F_DFORCE | F_FORCING | F_SSM | F_DSM | F_ACTIONS;
+
 // energy-spectrum row in the reference's float32 chain (Burger.py:562 on complex64 data)
 __device__ __forceinline__ float ek_row_f32(float re, float im, int N, float dxf) {
     const float en = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
     return __fmul_rn(en * (0.5f / (float)N), dxf);
 }
 
-template <typename T, int N>
+template <typename T, int N, int TS_, int SF>
 struct BurgersWarp {
-    using R = RealFFT<T, N>;
-    static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1;
-    static constexpr unsigned TEAM_MASK = TS == 32 ? 0xffffffffu : ((1u << TS) - 1u);
+    using R = RealFFT<T, N, TS_>;
+    static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
 
+    // all cross-lane traffic is scoped to the team (f.c.tmask): teams share a warp but never
+    // each other's control flow or data
     __device__ __forceinline__ static bool team_any(const R& f, bool pred) {
-        const unsigned b = __ballot_sync(0xffffffffu, pred);
-        return ((b >> f.c.base) & TEAM_MASK) != 0u;
+        return __ballot_sync(f.c.tmask, pred) != 0u;
     }
-    __device__ __forceinline__ static T team_sum(T x) {
+    __device__ __forceinline__ static T team_sum(const R& f, T x) {
 #pragma unroll
-        for (int h = TS / 2; h >= 1; h >>= 1) x += shfl_xor(x, h);
+        for (int h = TS / 2; h >= 1; h >>= 1) x += shfl_xor(x, h, f.c.tmask);
         return x;
     }
     // Real field stored as x[p] = (x_{2j}, x_{2j+1}), j = p*TS + tl.  Returns the left
@@ -44,14 +49,24 @@ struct BurgersWarp {
     // (x_{2j+2}), periodic.
     __device__ __forceinline__ static void halo(const R& f, const Cx<T> (&x)[P], T (&left)[P], T (&right)[P]) {
         const int tl = f.c.tl;
-        const int lr = f.c.base + ((tl + 1) & (TS - 1));
-        const int ll = f.c.base + ((tl - 1) & (TS - 1));
+        if constexpr (TS == 1) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const T a = shfl(x[p].re, lr), b = shfl(x[(p + 1) % P].re, lr);
-            right[p] = (tl == TS - 1) ? b : a;
-            const T c = shfl(x[p].im, ll), d = shfl(x[(p + P - 1) % P].im, ll);
-            left[p] = (tl == 0) ? d : c;
+            for (int p = 0; p < P; ++p) { right[p] = x[(p + 1) % P].re; left[p] = x[(p + P - 1) % P].im; }
+        } else {
+            const int lr = f.c.base + ((tl + 1) & (TS - 1));
+            const int ll = f.c.base + ((tl - 1) & (TS - 1));
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if constexpr (P == 1) {
+                    right[p] = shfl(x[p].re, lr, f.c.tmask);
+                    left[p] = shfl(x[p].im, ll, f.c.tmask);
+                } else {
+                    const T a = shfl(x[p].re, lr, f.c.tmask), b = shfl(x[(p + 1) % P].re, lr, f.c.tmask);
+                    right[p] = (tl == TS - 1) ? b : a;
+                    const T c = shfl(x[p].im, ll, f.c.tmask), d = shfl(x[(p + P - 1) % P].im, ll, f.c.tmask);
+                    left[p] = (tl == 0) ? d : c;
+                }
+            }
         }
     }
     // float64 -> float32 -> float64 (quirk Q1: the forcing accumulator of the reference is
@@ -62,7 +77,6 @@ struct BurgersWarp {
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
         const int wpc = blockDim.x >> 5;
-        constexpr int TPW = 32 / TS;
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
         if (first >= prm.B) return;                                  // whole warp idle
         R f;
@@ -72,7 +86,7 @@ struct BurgersWarp {
         const int64_t e = first + team;
         const bool has = e < prm.B;
         const int64_t ec = has ? e : 0;
-        const int flags = prm.flags;
+        const int flags = SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF);
         const bool q1 = !(flags & F_FORCING);
         const int scr = max(prm.M, 2 * N + N / 2);
         T* scratch = smem + (size_t)(warp * TPW + team) * scr;
@@ -80,23 +94,34 @@ struct BurgersWarp {
         // ---- per-register constants -------------------------------------------------------
         const T dt = prm.dt;
         const T nu = prm.nu[ec];
+        const T invN = T(1) / T(N);
         int kk[P];
-        T kw[P], g1[P], g2[P], g3[P];       // (1-C)/(1+C), dt/(1+C), 1/(1+C); C = nu k^2 dt/2 (Burger.py:486-488)
+        T kw[P], cv[P], cfo[P], cfn[P], cF[P];
+        // v' = [(1-C) v - dt/2 (3 Fn - Fn_old) + dt F] / (1+C),  C = nu k^2 dt / 2  (Burger.py:486-488)
+        //    = cv v + cfo Fn_old + cfn Fn + cF (dt F)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             kk[p] = f.k(p);
             kw[p] = prm.kwave[kk[p]];
             const T C = T(0.5) * (kw[p] * kw[p]) * nu * dt;
-            g1[p] = (T(1) - C) / (T(1) + C);
-            g2[p] = dt / (T(1) + C);
-            g3[p] = T(1) / (T(1) + C);
+            const T r = T(1) / (T(1) + C);
+            cv[p] = (T(1) - C) * r;
+            cfo[p] = T(0.5) * dt * r;
+            cfn[p] = T(-1.5) * dt * r;
+            cF[p] = q1 ? r : dt * r;
         }
         const T kwN = prm.kwave[H];
         const T CN = T(0.5) * (kwN * kwN) * nu * dt;
-        const T g1N = (T(1) - CN) / (T(1) + CN), g2N = dt / (T(1) + CN), g3N = T(1) / (T(1) + CN);
+        const T rN = T(1) / (T(1) + CN);
+        const T cvN = (T(1) - CN) * rN, cfoN = T(0.5) * dt * rN, cfnN = T(-1.5) * dt * rN, cFN = q1 ? rN : dt * rN;
+        Cx<T> ws_nl[P], ws1[P];
+        const T scale_nl = T(0.5) * invN * invN;        // u is kept as U = N u in registers
+        f.scaled_twiddles(scale_nl, ws_nl);
+        f.scaled_twiddles(T(1), ws1);
 
         // ---- load state ---------------------------------------------------------------------
-        bool live = has && prm.status[ec] == 0;
+        const bool was_live = has && prm.status[ec] == 0;
+        bool live = was_live;
         int iout = prm.iout[ec];
         T tnow = prm.tnow[ec];
         Cx<T> v[P], fn[P];
@@ -111,16 +136,17 @@ struct BurgersWarp {
         T fnN = ldcx(prm.fn + ec * NH + H).im;
         const T v0im = v[0].im;                 // meaningful on the dc lane only
 
-        // ---- u = Re ifft(v) -------------------------------------------------------------------
-        const T invN = T(1) / T(N);
-        Cx<T> u[P], uprev[P];
-        f.inv(v, vN.re, u, invN);
+        // ---- U = N * Re ifft(v) ---------------------------------------------------------------
+        Cx<T> U[P], Uprev[P];
+        f.inv(v, vN.re, U);
 #pragma unroll
-        for (int p = 0; p < P; ++p) uprev[p] = u[p];
+        for (int p = 0; p < P; ++p) Uprev[p] = U[p];
         if ((flags & F_NO_ADVANCE) && prm.version == 1 && iout > 0) {
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                uprev[p] = ldcx(reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N) + p * TS + tl);
+            for (int p = 0; p < P; ++p) {
+                const Cx<T> t = ldcx(reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N) + p * TS + tl);
+                Uprev[p] = cx<T>(t.re * T(N), t.im * T(N));
+            }
         }
 
         // ---- action field a @ basis (Burger.py:442) --------------------------------------------
@@ -130,7 +156,7 @@ struct BurgersWarp {
         for (int p = 0; p < P; ++p) { fa[p] = cx<T>(0, 0); Fa[p] = cx<T>(0, 0); }
         if (flags & F_ACTIONS) {
             for (int i = tl; i < prm.M; i += TS) scratch[i] = prm.actions[ec * prm.M + i];
-            __syncwarp();
+            __syncwarp(f.c.tmask);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 T val[2];
@@ -148,13 +174,29 @@ struct BurgersWarp {
                 }
                 fa[p] = cx<T>(val[0], val[1]);
             }
-            __syncwarp();
+            __syncwarp(f.c.tmask);
             if (flags & F_DFORCE) {           // spectrum of a direct forcing is constant over the sub-steps
                 Cx<T> z[P];
 #pragma unroll
                 for (int p = 0; p < P; ++p) z[p] = fa[p];
-                f.fwd(z, Fa, FaN, T(1));
+                f.fwd(z, Fa, FaN, T(1), ws1);
+            } else {                          // eddy viscosity: fold 1/dx^2 and the 1/N of U once
+                const T s = invN / (prm.dx * prm.dx);
+#pragma unroll
+                for (int p = 0; p < P; ++p) fa[p] = cx<T>(fa[p].re * s, fa[p].im * s);
             }
+        }
+
+        // ---- stochastic forcing spectrum (Burger.py:410-421): non-zero at k = 1,2,3 only ----------
+        Cx<T> Fc[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) Fc[p] = cx<T>(0, 0);
+        const Cx<T>* fc_row = prm.fcoef + ((flags & F_FORCING_PER_ENV) ? ec : 0) * prm.stepper * 3;
+        int col = (flags & F_FORCING) ? iout % prm.stepper : 0;      // column ioutnum % stepper (Q3)
+        if ((flags & F_FORCING) && prm.stepper == 1) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (kk[p] >= 1 && kk[p] <= 3) Fc[p] = ldcx(fc_row + (kk[p] - 1));
         }
 
         // ---- reward bookkeeping ----------------------------------------------------------------
@@ -169,6 +211,7 @@ struct BurgersWarp {
         const T inv_dx = T(1) / prm.dx, inv_dx2 = T(1) / (prm.dx * prm.dx);
         const int64_t truth_base =
             prm.truth ? ((prm.truth_map ? prm.truth_map[ec] : 0) * prm.truth_rows) : 0;
+        bool bad = false;
 
         // =============================== sub-steps ==============================================
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
@@ -177,8 +220,8 @@ struct BurgersWarp {
             Cx<T> z[P], X[P];
             T XN;
 #pragma unroll
-            for (int p = 0; p < P; ++p) z[p] = cx<T>(u[p].re * u[p].re, u[p].im * u[p].im);
-            f.fwd(z, X, XN, T(0.5));
+            for (int p = 0; p < P; ++p) z[p] = cx<T>(U[p].re * U[p].re, U[p].im * U[p].im);
+            f.fwd(z, X, XN, scale_nl, ws_nl);
 
             Cx<T> Fh[P];
             T FhN = T(0);
@@ -187,17 +230,16 @@ struct BurgersWarp {
 
             T left[P], right[P];
             const bool need_nb = (flags & (F_SSM | F_DSM)) || ((flags & F_ACTIONS) && !(flags & F_DFORCE));
-            if (need_nb) halo(f, u, left, right);
+            if (need_nb) halo(f, U, left, right);
 
             if (flags & (F_SSM | F_DSM)) {
-                Cx<T> sgs[P];
-                Cx<T> dudx[P], d2[P];
+                Cx<T> sgs[P], dudx[P], d2[P];
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     // upwind first difference, centred second difference (Burger.py:342-346)
-                    dudx[p] = cx<T>((u[p].re - left[p]) * inv_dx, (u[p].im - u[p].re) * inv_dx);
-                    d2[p] = cx<T>((u[p].im - T(2) * u[p].re + left[p]) * inv_dx2,
-                                  (right[p] - T(2) * u[p].im + u[p].re) * inv_dx2);
+                    const T ue = U[p].re * invN, uo = U[p].im * invN, ul = left[p] * invN, ur = right[p] * invN;
+                    dudx[p] = cx<T>((ue - ul) * inv_dx, (uo - ue) * inv_dx);
+                    d2[p] = cx<T>((uo - T(2) * ue + ul) * inv_dx2, (ur - T(2) * uo + ue) * inv_dx2);
                 }
                 if (flags & F_SSM) {
                     // Burger.py:339-349, delta = 2 pi / N whatever L is
@@ -218,31 +260,36 @@ struct BurgersWarp {
 #pragma unroll
                     for (int p = 0; p < P; ++p)      // filtered fft(u^2) = 2 X
                         w[p] = cut[p] ? cx<T>(0, 0) : cx<T>(T(2) * X[p].re, T(2) * X[p].im);
-                    f.inv(w, cutN ? T(0) : T(2) * XN, L1, T(0.5) * invN);
+                    f.inv(w, cutN ? T(0) : T(2) * XN, L1);
 #pragma unroll
-                    for (int p = 0; p < P; ++p)
+                    for (int p = 0; p < P; ++p) {
+                        L1[p] = cx<T>(L1[p].re * (T(0.5) * invN), L1[p].im * (T(0.5) * invN));
                         if (cut[p]) v[p] = cx<T>(0, 0);
+                    }
                     if (cutN) vN = cx<T>(0, 0);
-                    f.inv(v, vN.re, uh, invN);
+                    f.inv(v, vN.re, uh);
 #pragma unroll
-                    for (int p = 0; p < P; ++p)
+                    for (int p = 0; p < P; ++p) {
+                        uh[p] = cx<T>(uh[p].re * invN, uh[p].im * invN);
                         z[p] = cx<T>(fabs(dudx[p].re) * dudx[p].re, fabs(dudx[p].im) * dudx[p].im);
+                    }
                     Cx<T> W2[P], M1[P];
                     T W2N;
-                    f.fwd(z, W2, W2N, T(1));
+                    f.fwd(z, W2, W2N, T(1), ws1);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         if (cut[p]) W2[p] = cx<T>(0, 0);
-                    f.inv(W2, cutN ? T(0) : W2N, M1, delta * delta * invN);
+                    f.inv(W2, cutN ? T(0) : W2N, M1);
                     T uhl[P], uhr[P];
                     halo(f, uh, uhl, uhr);
                     Cx<T> malt[P];
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
+                        const T m1a = delta * delta * invN * M1[p].re, m1b = delta * delta * invN * M1[p].im;
                         const T da = (uh[p].re - uhl[p]) * inv_dx, db = (uh[p].im - uh[p].re) * inv_dx;
                         const T M2a = deltah * deltah * fabs(da) * da, M2b = deltah * deltah * fabs(db) * db;
-                        malt[p] = cx<T>(T(4) / (deltah * deltah) * M2a - T(1) / (delta * delta) * M1[p].re,
-                                        T(4) / (deltah * deltah) * M2b - T(1) / (delta * delta) * M1[p].im);
+                        malt[p] = cx<T>(T(4) / (deltah * deltah) * M2a - T(1) / (delta * delta) * m1a,
+                                        T(4) / (deltah * deltah) * M2b - T(1) / (delta * delta) * m1b);
                     }
                     T ml[P], mr[P];
                     halo(f, malt, ml, mr);
@@ -255,8 +302,8 @@ struct BurgersWarp {
                         num += -Lga * Mga - Lgb * Mgb;
                         den += Mga * Mga + Mgb * Mgb;
                     }
-                    num = team_sum(num);
-                    den = team_sum(den);
+                    num = team_sum(f, num);
+                    den = team_sum(f, den);
                     const T c = num / den;          // mean/mean: the 1/N cancels (Burger.py:397)
 #pragma unroll
                     for (int p = 0; p < P; ++p)
@@ -264,23 +311,22 @@ struct BurgersWarp {
                 }
                 Cx<T> S[P];
                 T SN;
-                f.fwd(sgs, S, SN, T(1));
+                f.fwd(sgs, S, SN, T(1), ws1);
 #pragma unroll
                 for (int p = 0; p < P; ++p) Fh[p] = q1 ? cx<T>(r32(S[p].re), r32(S[p].im)) : S[p];
                 FhN = q1 ? r32(SN) : SN;
             }
 
             if (flags & F_FORCING) {
-                // Burger.py:410-421: the spectrum of sum_k c_k cos(...) is non-zero at k = +-1,2,3 only;
-                // it REPLACES whatever the closures accumulated (Q2).  Column ioutnum % stepper (Q3).
-                const int64_t row = (flags & F_FORCING_PER_ENV) ? ec : 0;
-                const int col = iout % prm.stepper;
+                // the forcing spectrum REPLACES whatever the closures accumulated (Q2)
+                if (prm.stepper > 1) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    Cx<T> c = cx<T>(0, 0);
-                    if (kk[p] >= 1 && kk[p] <= 3) c = ldcx(prm.fcoef + (row * prm.stepper + col) * 3 + (kk[p] - 1));
-                    Fh[p] = c;
+                    for (int p = 0; p < P; ++p)
+                        if (kk[p] >= 1 && kk[p] <= 3) Fc[p] = ldcx(fc_row + col * 3 + (kk[p] - 1));
+                    col = (col + 1 == prm.stepper) ? 0 : col + 1;
                 }
+#pragma unroll
+                for (int p = 0; p < P; ++p) Fh[p] = Fc[p];
                 FhN = T(0);
             }
 
@@ -295,9 +341,9 @@ struct BurgersWarp {
                     // eddy-viscosity action: forcing = (a @ basis) * d2u/dx2 (Burger.py:445-450)
 #pragma unroll
                     for (int p = 0; p < P; ++p)
-                        z[p] = cx<T>(fa[p].re * ((left[p] - T(2) * u[p].re + u[p].im) * inv_dx2),
-                                     fa[p].im * ((u[p].re - T(2) * u[p].im + right[p]) * inv_dx2));
-                    f.fwd(z, S, SN, T(1));
+                        z[p] = cx<T>(fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
+                                     fa[p].im * (U[p].re - T(2) * U[p].im + right[p]));
+                    f.fwd(z, S, SN, T(1), ws1);
                 }
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -307,63 +353,50 @@ struct BurgersWarp {
                 FhN = q1 ? r32(FhN + SN) : FhN + SN;
             }
 
-            // ABCN update (Burger.py:486-489): v <- ((1-C) v - dt/2 (3 Fn - Fn_old) + dt F) / (1+C).
-            // Q1 (cont.): while the forcing accumulator is complex64, `self.dt*Fforcing` is a
-            // complex64 product: float32(dt) * float32(F), rounded to float32.
-            Cx<T> vn[P], fnn[P];
-            bool bad = false;
+            // ABCN update.  Q1 (cont.): while the forcing accumulator is complex64, `self.dt*Fforcing`
+            // (Burger.py:488) is a complex64 product: float32(dt) * float32(F), rounded to float32.
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                fnn[p] = cx<T>(-kw[p] * X[p].im, kw[p] * X[p].re);                       // i k X
-                const Cx<T> dtF = q1 ? cx<T>((T)__fmul_rn(dtf, (float)Fh[p].re), (T)__fmul_rn(dtf, (float)Fh[p].im))
-                                     : cx<T>(dt * Fh[p].re, dt * Fh[p].im);
-                const T tr = T(0.5) * fn[p].re - T(1.5) * fnn[p].re;
-                const T ti = T(0.5) * fn[p].im - T(1.5) * fnn[p].im;
-                vn[p] = cx<T>(fma(g3[p], dtF.re, fma(g2[p], tr, g1[p] * v[p].re)),
-                              fma(g3[p], dtF.im, fma(g2[p], ti, g1[p] * v[p].im)));
-                bad |= blown(vn[p]);
+                Uprev[p] = U[p];
+                const Cx<T> fnn = cx<T>(-kw[p] * X[p].im, kw[p] * X[p].re);                // i k X
+                const Cx<T> F = q1 ? cx<T>((T)__fmul_rn(dtf, (float)Fh[p].re), (T)__fmul_rn(dtf, (float)Fh[p].im)) : Fh[p];
+                v[p] = cx<T>(fma(cF[p], F.re, fma(cfn[p], fnn.re, fma(cfo[p], fn[p].re, cv[p] * v[p].re))),
+                             fma(cF[p], F.im, fma(cfn[p], fnn.im, fma(cfo[p], fn[p].im, cv[p] * v[p].im))));
+                fn[p] = fnn;
+                bad |= blown(v[p]);
             }
-            // k = 0: Fn = 0, F real -> Im v[0] is a constant of the motion; Nyquist: F real, Fn imaginary
-            const T fnnN = kwN * XN;
-            const T dtFN = q1 ? (T)__fmul_rn(dtf, (float)FhN) : dt * FhN;
-            const Cx<T> vnN = cx<T>(fma(g3N, dtFN, g1N * vN.re), fma(g2N, T(0.5) * fnN - T(1.5) * fnnN, g1N * vN.im));
-            if (f.dc) {
-                vn[0].im = v0im;
-                bad |= blown(vnN);
-            }
-            bad = team_any(f, bad);
-            if (live && bad) { prm.status[e] = 1; live = false; }
-            if (live) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) { v[p] = vn[p]; fn[p] = fnn[p]; uprev[p] = u[p]; }
-                vN = vnN;
+            {   // k = 0: Fn = 0, F real -> Im v[0] is a constant of the motion; Nyquist: F real, Fn imaginary
+                const T fnnN = kwN * XN;
+                const T FN = q1 ? (T)__fmul_rn(dtf, (float)FhN) : FhN;
+                vN = cx<T>(fma(cFN, FN, cvN * vN.re), fma(cfnN, fnnN, fma(cfoN, fnN, cvN * vN.im)));
                 fnN = fnnN;
-                iout += 1;
-                tnow += dt;
-            }
-            // u = Re ifft(v) (Burger.py:491); a blown-up env keeps its last good field
-            {
-                Cx<T> un[P];
-                f.inv(v, vN.re, un, invN);
-                if (live) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p) u[p] = un[p];
+                if (f.dc) {
+                    v[0].im = v0im;
+                    bad |= blown(vN);
                 }
             }
+            iout += 1;
+            tnow += dt;
 
-            if (live) {
-                // float32 spectrum chain (Q6): Ek row from complex64(v), sequential float32 sum
+            // U = N Re ifft(v) (Burger.py:491)
+            f.inv(v, vN.re, U);
+
+            // float32 spectrum chain (Q6): Ek row from complex64(v), sequential float32 sum
 #pragma unroll
-                for (int p = 0; p < P; ++p)
-                    acc32[p] = __fadd_rn(acc32[p], ek_row_f32((float)v[p].re, (float)v[p].im, N, dxf));
-                accN = __fadd_rn(accN, ek_row_f32((float)vN.re, (float)vN.im, N, dxf));
+            for (int p = 0; p < P; ++p)
+                acc32[p] = __fadd_rn(acc32[p], ek_row_f32((float)v[p].re, (float)v[p].im, N, dxf));
+            accN = __fadd_rn(accN, ek_row_f32((float)vN.re, (float)vN.im, N, dxf));
 
-                if (prm.hist_rows > 0 && iout < prm.hist_rows) {
+            if (prm.hist_rows > 0) {
+                // blow-up semantics: rows are only written while the env is healthy
+                live = live && !team_any(f, bad);
+                if (live && iout < prm.hist_rows) {
                     const int64_t hrow = e * prm.hist_rows + iout;
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const int j = p * TS + tl;
-                        if (prm.uu_hist) stcx(reinterpret_cast<Cx<T>*>(prm.uu_hist + hrow * N) + j, u[p]);
+                        if (prm.uu_hist)
+                            stcx(reinterpret_cast<Cx<T>*>(prm.uu_hist + hrow * N) + j, cx<T>(U[p].re * invN, U[p].im * invN));
                         if (prm.vv_hist) {
                             Cx<float> c; c.re = (float)v[p].re; c.im = (float)v[p].im;
                             prm.vv_hist[hrow * N + kk[p]] = c;
@@ -376,30 +409,37 @@ struct BurgersWarp {
                         if (prm.ektt_hist) prm.ektt_hist[hrow * NH + H] = (double)accN / (double)(iout + 1);
                     }
                 }
+            }
 
-                if (prm.reward_mode == REWARD_MSE && prm.truth) {
-                    // Burger.py:589-599 after every sub-step, averaged over them (burger_environment.py:153)
-                    const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
-                    const Cx<T>* tr = reinterpret_cast<const Cx<T>*>(prm.truth + (truth_base + row) * N);
+            if (prm.reward_mode == REWARD_MSE && prm.truth) {
+                // Burger.py:589-599 after every sub-step, averaged over them (burger_environment.py:153)
+                const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
+                const Cx<T>* tr = reinterpret_cast<const Cx<T>*>(prm.truth + (truth_base + row) * N);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const Cx<T> t = ldcx(tr + p * TS + tl);
-                        const T da = t.re - u[p].re, db = t.im - u[p].im;
-                        mse[p].re += da * da;
-                        mse[p].im += db * db;
-                    }
+                for (int p = 0; p < P; ++p) {
+                    const Cx<T> t = ldcx(tr + p * TS + tl);
+                    const T da = t.re - U[p].re * invN, db = t.im - U[p].im * invN;
+                    mse[p].re += da * da;
+                    mse[p].im += db * db;
                 }
             }
         }
 
         // =============================== epilogue ===============================================
+        // A blown-up environment (non-finite / > FLT_MAX spectrum, the reference's FloatingPointError)
+        // keeps the state it had before this call and is marked TRUNCATED.
+        if (nsub > 0) {
+            const bool blew = team_any(f, bad);
+            if (was_live && blew && f.dc) prm.status[e] = 1;
+            live = live && !blew;
+        }
         if (nsub > 0 && live) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 stcx(prm.v + e * NH + kk[p], v[p]);
                 stcx(prm.fn + e * NH + kk[p], fn[p]);
                 prm.acc[e * NH + kk[p]] = acc32[p];
-                stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, uprev[p]);
+                stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
             }
             if (f.dc) {
                 stcx(prm.v + e * NH + H, vN);
@@ -416,27 +456,29 @@ struct BurgersWarp {
             // version / agent-window layout becomes one coalesced row store
             const int ver = prm.version, A = prm.A;
             T left[P], right[P];
-            halo(f, u, left, right);
-            __syncwarp();
+            halo(f, U, left, right);
+            __syncwarp(f.c.tmask);
             T* f0 = scratch;
             T* f1 = f0 + N;
             T* ek = f1 + N;
+            const T sd2 = inv_dx2 * invN, sdt = invN / dt;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int j = p * TS + tl;
-                const Cx<T> d2 = cx<T>((left[p] - T(2) * u[p].re + u[p].im) * inv_dx2,
-                                       (u[p].re - T(2) * u[p].im + right[p]) * inv_dx2);
-                const Cx<T> dudt = cx<T>((u[p].re - uprev[p].re) / dt, (u[p].im - uprev[p].im) / dt);
+                const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
+                const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2,
+                                       (U[p].re - T(2) * U[p].im + right[p]) * sd2);
+                const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
                 Cx<T> a = d2, b = d2;
                 if (ver == 1) { a = dudt; }
-                else if (ver == 2) { a = u[p]; b = cx<T>(u[p].re * u[p].re, u[p].im * u[p].im); }
-                else if (ver == 4) { a = u[p]; }
+                else if (ver == 2) { a = u; b = cx<T>(u.re * u.re, u.im * u.im); }
+                else if (ver == 4) { a = u; }
                 stcx(reinterpret_cast<Cx<T>*>(f0) + j, a);
                 stcx(reinterpret_cast<Cx<T>*>(f1) + j, b);
                 // Burger.py:653, from the live float64 v
                 ek[kk[p]] = T(0.5) * ((v[p].re * v[p].re + v[p].im * v[p].im) / T(N)) * prm.dx;
             }
-            __syncwarp();
+            __syncwarp(f.c.tmask);
             const int nf = (ver == 1 || ver == 2) ? 2 : 1;
             const int seg = A == 1 ? N : N / A + 2;
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
@@ -457,7 +499,7 @@ struct BurgersWarp {
                     prm.state_out[e * S + o] = live ? val : inf;          // Burger.py:633-643
                 }
             }
-            __syncwarp();
+            __syncwarp(f.c.tmask);
         }
 
         if (prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0) {
@@ -474,7 +516,7 @@ struct BurgersWarp {
                     const T q = fabs(ed - es) / ed;
                     part += q * q;
                 }
-            part = team_sum(part) / T(H - 1);
+            part = team_sum(f, part) / T(H - 1);
             const T prev = prm.kprev[ec];
             const T r = live ? prev - part : -inf;
             if (has) {
@@ -484,20 +526,20 @@ struct BurgersWarp {
         }
         if (prm.reward_out && prm.reward_mode == REWARD_MSE && prm.truth) {
             const int A = prm.A, W = N / A;
-            if (nsub == 0 && live) {     // getMseReward() of the current state (Burger.py:578-601)
+            if (nsub == 0) {             // getMseReward() of the current state (Burger.py:578-601)
                 const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
                 const Cx<T>* tr = reinterpret_cast<const Cx<T>*>(prm.truth + (truth_base + row) * N);
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     const Cx<T> t = ldcx(tr + p * TS + tl);
-                    const T da = t.re - u[p].re, db = t.im - u[p].im;
+                    const T da = t.re - U[p].re * invN, db = t.im - U[p].im * invN;
                     mse[p] = cx<T>(da * da, db * db);
                 }
             }
-            __syncwarp();
+            __syncwarp(f.c.tmask);
 #pragma unroll
             for (int p = 0; p < P; ++p) stcx(reinterpret_cast<Cx<T>*>(scratch) + p * TS + tl, mse[p]);
-            __syncwarp();
+            __syncwarp(f.c.tmask);
             if (has) {
                 for (int a = tl; a < A; a += TS) {       // agent a owns points [a N/A, (a+1) N/A)
                     T sum = T(0);

@@ -34,12 +34,16 @@ template <typename T> __device__ __forceinline__ void stcx(Cx<T>* p, Cx<T> a) {
     *reinterpret_cast<typename Vec2<T>::type*>(p) = v;
 }
 
-__device__ __forceinline__ double shfl(double v, int src, unsigned mask = 0xffffffffu) { return __shfl_sync(mask, v, src); }
-__device__ __forceinline__ float shfl(float v, int src, unsigned mask = 0xffffffffu) { return __shfl_sync(mask, v, src); }
-__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-template <typename T> __device__ __forceinline__ Cx<T> shfl_xor(Cx<T> v, int m) { return cx<T>(shfl_xor(v.re, m), shfl_xor(v.im, m)); }
-template <typename T> __device__ __forceinline__ Cx<T> shfl(Cx<T> v, int src) { return cx<T>(shfl(v.re, src), shfl(v.im, src)); }
+__device__ __forceinline__ double shfl(double v, int src, unsigned mask) { return __shfl_sync(mask, v, src); }
+__device__ __forceinline__ float shfl(float v, int src, unsigned mask) { return __shfl_sync(mask, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m, unsigned mask) { return __shfl_xor_sync(mask, v, m); }
+__device__ __forceinline__ float shfl_xor(float v, int m, unsigned mask) { return __shfl_xor_sync(mask, v, m); }
+template <typename T> __device__ __forceinline__ Cx<T> shfl_xor(Cx<T> v, int m, unsigned mask) {
+    return cx<T>(shfl_xor(v.re, m, mask), shfl_xor(v.im, m, mask));
+}
+template <typename T> __device__ __forceinline__ Cx<T> shfl(Cx<T> v, int src, unsigned mask) {
+    return cx<T>(shfl(v.re, src, mask), shfl(v.im, src, mask));
+}
 
 // The reference traps overflow when it casts v to complex64 for its history
 // (Burger.py:8,498 / KS.py:7,273): an env is "blown up" as soon as a component of v

@@ -6,9 +6,15 @@
 #include "params.h"
 #include "pack.cuh"
 
+#ifndef MPDE_WARPS_PER_SMSP_TARGET
+#define MPDE_WARPS_PER_SMSP_TARGET 2
+#endif
+
 namespace mpde {
 
 template <typename T> int launch_burgers(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_cta(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T>
 int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,

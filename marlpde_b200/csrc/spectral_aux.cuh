@@ -3,7 +3,7 @@
 #pragma once
 #include "params.h"
 #include "warp_fft.cuh"
-#include "burgers_warp.cuh"
+#include "burgers_warp.cuh"   // ek_row_f32
 
 namespace mpde {
 
@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(128) aux_warp_kernel(const SpectralParams<T> p
 #pragma unroll
         for (int p = 0; p < P; ++p) { u[p] = ldcx(src + p * TS + tl); z[p] = u[p]; }
         T nyq;
-        f.fwd(z, v, nyq, T(1));
+        Cx<T> ws1[P];
+        f.scaled_twiddles(T(1), ws1);
+        f.fwd(z, v, nyq, T(1), ws1);
         vN = cx<T>(nyq, T(0));
     } else {
         if constexpr (MODE == AUX_RESET_V) {
@@ -56,7 +58,9 @@ __global__ void __launch_bounds__(128) aux_warp_kernel(const SpectralParams<T> p
             for (int p = 0; p < P; ++p) v[p] = ldcx(prm.v + ec * NH + kk[p]);
             vN = ldcx(prm.v + ec * NH + H);
         }
-        f.inv(v, vN.re, u, invN);
+        f.inv(v, vN.re, u);
+#pragma unroll
+        for (int p = 0; p < P; ++p) u[p] = cx<T>(u[p].re * invN, u[p].im * invN);
     }
 
     if constexpr (MODE == AUX_GET_U) {
@@ -74,7 +78,9 @@ __global__ void __launch_bounds__(128) aux_warp_kernel(const SpectralParams<T> p
             Cx<T> z[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) z[p] = cx<T>(u[p].re * u[p].re, u[p].im * u[p].im);
-            f.fwd(z, X, XN, T(0.5));
+            Cx<T> wsh[P];
+            f.scaled_twiddles(T(0.5), wsh);
+            f.fwd(z, X, XN, T(0.5), wsh);
         }
         if (!sel) return;
         const float dxf = (float)prm.dx;

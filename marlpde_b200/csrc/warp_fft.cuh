@@ -25,11 +25,13 @@ __host__ __device__ constexpr int brev_bits(int x, int bits) {
     return r;
 }
 
-// TWS: stride into the twiddle table (table holds exp(-2 pi i j / (H*TWS)))
-template <typename T, int H, int TWS = 1>
+// TS_: lanes per sequence (team size); TWS: stride into the twiddle table (table holds
+// exp(-2 pi i j / (H*TWS)))
+template <typename T, int H, int TS_ = (H < 32 ? H : 32), int TWS = 1>
 struct WarpFFT {
-    static constexpr int TS = H < 32 ? H : 32;
+    static constexpr int TS = TS_;
     static constexpr int P = H / TS;
+    static_assert(TS >= 1 && TS <= 32 && (TS & (TS - 1)) == 0 && TS <= H, "team size: power of two, <= 32, <= H");
     static constexpr int LOGH = ilog2(H);
     static constexpr int LOGTS = ilog2(TS);
     static constexpr int LOGP = ilog2(P);
@@ -37,6 +39,8 @@ struct WarpFFT {
 
     int tl;                         // lane within the team
     int base;                       // first lane of the team within the warp
+    unsigned tmask;                 // lanes of this team: every shuffle is team-scoped, so teams never
+                                    // depend on each other's control flow (a team may be idle or dead)
     Cx<T> wx[LOGTS > 0 ? LOGTS : 1];  // cross-lane twiddles, (1,0) on the lower lane of a pair
     Cx<T> wl[P > 1 ? P - 1 : 1];    // in-register twiddles
     int part[P];                    // lane holding wavenumber -k (mod H) for register pp(p)
@@ -54,6 +58,7 @@ struct WarpFFT {
         const int lane = threadIdx.x & 31;
         tl = lane & (TS - 1);
         base = lane & ~(TS - 1);
+        tmask = TS == 32 ? 0xffffffffu : (((1u << TS) - 1u) << base);
 #pragma unroll
         for (int s = 0; s < LOGTS; ++s) {
             const int h = TS >> (s + 1);
@@ -94,7 +99,7 @@ struct WarpFFT {
             const T sg = (tl & h) ? T(-1) : T(1);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const Cx<T> o = shfl_xor(z[p], h);
+                const Cx<T> o = shfl_xor(z[p], h, tmask);
                 const Cx<T> t = cx<T>(fma(sg, z[p].re, o.re), fma(sg, z[p].im, o.im));
                 z[p] = (h == 1) ? t : cmul(t, wx[s]);          // last stage: twiddle is 1
             }
@@ -106,12 +111,12 @@ struct WarpFFT {
 #pragma unroll
         for (int s = LOGTS - 1; s >= 0; --s) {
             const int h = TS >> (s + 1);
-            const bool up = (tl & h) != 0;
+            const T sg = (tl & h) ? T(-1) : T(1);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const Cx<T> m = (h == 1) ? z[p] : cmulc(z[p], wx[s]);
-                const Cx<T> o = shfl_xor(m, h);
-                z[p] = up ? (o - m) : (m + o);
+                const Cx<T> o = shfl_xor(m, h, tmask);
+                z[p] = cx<T>(fma(sg, m.re, o.re), fma(sg, m.im, o.im));
             }
         }
         if constexpr (P > 1) {
@@ -129,13 +134,16 @@ struct WarpFFT {
     }
 
     // value held for wavenumber -k (mod H) by the team, for the k of register p
-    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[P], int p) const { return shfl(z[pp(p)], part[p]); }
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[P], int p) const {
+        if constexpr (TS == 1) return z[pp(p)];
+        else return shfl(z[pp(p)], part[p], tmask);
+    }
 };
 
-template <typename T, int N>
+template <typename T, int N, int TS_ = (N / 2 < 32 ? N / 2 : 32)>
 struct RealFFT {
     static constexpr int H = N / 2;
-    using C = WarpFFT<T, H, 2>;
+    using C = WarpFFT<T, H, TS_, 2>;
     static constexpr int TS = C::TS, P = C::P;
     static_assert(N >= 8 && N <= 256, "warp-resident real FFT handles N = 8..256");
 
@@ -154,7 +162,8 @@ struct RealFFT {
 
     // z[p] = (x_{2j}, x_{2j+1}), j = p*TS + tl   ->   X[p] = scale * fft(x)[k(p)],
     // nyq = scale * fft(x)[N/2] (real; meaningful on the dc lane only).  z is clobbered.
-    __device__ __forceinline__ void fwd(Cx<T> (&z)[P], Cx<T> (&X)[P], T& nyq, T scale) const {
+    // ws[p] must hold (scale/2) * wk[p] (pre-scaled by the caller, once per kernel).
+    __device__ __forceinline__ void fwd(Cx<T> (&z)[P], Cx<T> (&X)[P], T& nyq, T scale, const Cx<T> (&ws)[P]) const {
         c.fwd(z);
         const T hs = T(0.5) * scale;
 #pragma unroll
@@ -162,26 +171,29 @@ struct RealFFT {
             const Cx<T> zp = c.mirrored(z, p);                                   // Z[H-k]
             const Cx<T> E = cx<T>(z[p].re + zp.re, z[p].im - zp.im);            // 2 * fft(x_even)[k]
             const Cx<T> O = cx<T>(z[p].im + zp.im, zp.re - z[p].re);            // 2 * fft(x_odd)[k]
-            const Cx<T> wO = cmul(wk[p], O);
-            X[p] = cx<T>((E.re + wO.re) * hs, (E.im + wO.im) * hs);
+            X[p] = cx<T>(fma(hs, E.re, fma(ws[p].re, O.re, -ws[p].im * O.im)),
+                         fma(hs, E.im, fma(ws[p].re, O.im, ws[p].im * O.re)));
             if (p == 0) nyq = (E.re - O.re) * hs;                                // k = 0: E, O real
         }
     }
-    // X[p] = spectrum at k(p), nyq = real Nyquist value (dc lane)  ->  z[p] = scale * N * ifft(X)
-    // at points (2j, 2j+1).  Only the real parts of X_0 and X_{N/2} enter (np.real(ifft(.))).
-    __device__ __forceinline__ void inv(const Cx<T> (&X)[P], T nyq, Cx<T> (&z)[P], T scale) const {
+    __device__ __forceinline__ void scaled_twiddles(T scale, Cx<T> (&ws)[P]) const {
+#pragma unroll
+        for (int p = 0; p < P; ++p) ws[p] = cx<T>(wk[p].re * (T(0.5) * scale), wk[p].im * (T(0.5) * scale));
+    }
+    // X[p] = spectrum at k(p), nyq = real Nyquist value (dc lane)  ->  z[p] = N * ifft(X) at points
+    // (2j, 2j+1), UNNORMALISED.  Only the real parts of X_0 and X_{N/2} enter (np.real(ifft(.))).
+    __device__ __forceinline__ void inv(const Cx<T> (&X)[P], T nyq, Cx<T> (&z)[P]) const {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const Cx<T> xp = c.mirrored(X, p);                                   // X[H-k]
             const Cx<T> E = cx<T>(X[p].re + xp.re, X[p].im - xp.im);
             const Cx<T> D = cx<T>(X[p].re - xp.re, X[p].im + xp.im);
-            const Cx<T> O = cmulc(D, wk[p]);
-            z[p] = cx<T>(E.re - O.im, E.im + O.re);
+            // z = E + i * (D * conj(wk))
+            z[p] = cx<T>(fma(-D.im, wk[p].re, fma(D.re, wk[p].im, E.re)),
+                         fma(D.re, wk[p].re, fma(D.im, wk[p].im, E.im)));
             if (p == 0 && dc) z[p] = cx<T>(X[p].re + nyq, X[p].re - nyq);
         }
         c.inv(z);
-#pragma unroll
-        for (int p = 0; p < P; ++p) { z[p].re *= scale; z[p].im *= scale; }
     }
 };
 
