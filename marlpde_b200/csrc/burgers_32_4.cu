@@ -1,0 +1,5 @@
+// Burgers step kernels for N = 32, 4 lanes per environment (all mode specialisations).
+#include "burgers_dispatch.cuh"
+namespace mpde {
+MPDE_INSTANTIATE_TEAM(32, 4)
+}

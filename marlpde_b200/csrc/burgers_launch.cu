@@ -1,7 +1,24 @@
-// Launchers of the Burgers environment step (Burger.py:333-499): grid sizes other than 32 / 64.
+// Launchers of the Burgers environment step (Burger.py:333-499).
 #include "burgers_dispatch.cuh"
 
 namespace mpde {
+
+template <typename T>
+static int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st) {
+    switch (pick_team(p.B, 32, 16, 4)) {
+        case 16: return launch_burgers_32_16<T>(p, st);
+        case 8: return launch_burgers_32_8<T>(p, st);
+        default: return launch_burgers_32_4<T>(p, st);
+    }
+}
+template <typename T>
+static int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st) {
+    switch (pick_team(p.B, 64, 32, 8)) {
+        case 32: return launch_burgers_64_32<T>(p, st);
+        case 16: return launch_burgers_64_16<T>(p, st);
+        default: return launch_burgers_64_8<T>(p, st);
+    }
+}
 
 template <typename T>
 int launch_burgers(const SpectralParams<T>& p, cudaStream_t st) {

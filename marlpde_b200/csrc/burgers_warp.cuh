@@ -29,7 +29,9 @@ __device__ __forceinline__ float ek_row_f32(float re, float im, int N, float dxf
     return __fmul_rn(en * (0.5f / (float)N), dxf);
 }
 
-template <typename T, int N, int TS_, int SF>
+// LEAN: compile-time promise of the common training configuration -- no history buffers, no MSE
+// truth table, forcing column period 1 -- which removes those branches from the sub-step loop.
+template <typename T, int N, int TS_, int SF, bool LEAN = false>
 struct BurgersWarp {
     using R = RealFFT<T, N, TS_>;
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
@@ -96,9 +98,9 @@ struct BurgersWarp {
         const T nu = prm.nu[ec];
         const T invN = T(1) / T(N);
         int kk[P];
-        T kw[P], cv[P], cfo[P], cfn[P], cF[P];
+        T kw[P], cv[P], cfo[P], cF[P];
         // v' = [(1-C) v - dt/2 (3 Fn - Fn_old) + dt F] / (1+C),  C = nu k^2 dt / 2  (Burger.py:486-488)
-        //    = cv v + cfo Fn_old + cfn Fn + cF (dt F)
+        //    = cv v + cfo (Fn_old - 3 Fn) + cF (dt F)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             kk[p] = f.k(p);
@@ -107,13 +109,12 @@ struct BurgersWarp {
             const T r = T(1) / (T(1) + C);
             cv[p] = (T(1) - C) * r;
             cfo[p] = T(0.5) * dt * r;
-            cfn[p] = T(-1.5) * dt * r;
             cF[p] = q1 ? r : dt * r;
         }
         const T kwN = prm.kwave[H];
         const T CN = T(0.5) * (kwN * kwN) * nu * dt;
         const T rN = T(1) / (T(1) + CN);
-        const T cvN = (T(1) - CN) * rN, cfoN = T(0.5) * dt * rN, cfnN = T(-1.5) * dt * rN, cFN = q1 ? rN : dt * rN;
+        const T cvN = (T(1) - CN) * rN, cfoN = T(0.5) * dt * rN, cFN = q1 ? rN : dt * rN;
         Cx<T> ws_nl[P], ws1[P];
         const T scale_nl = T(0.5) * invN * invN;        // u is kept as U = N u in registers
         f.scaled_twiddles(scale_nl, ws_nl);
@@ -215,22 +216,35 @@ struct BurgersWarp {
 
         // =============================== sub-steps ==============================================
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
+        const bool hist = !LEAN && prm.hist_rows > 0;
+        const bool do_mse = !LEAN && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
+        const bool multi_col = !LEAN && prm.stepper > 1;
+        const bool eddy = (flags & F_ACTIONS) && !(flags & F_DFORCE);
         for (int it = 0; it < nsub; ++it) {
-            // nonlinear term: X = fft(u^2 / 2) (Burger.py:487)
-            Cx<T> z[P], X[P];
-            T XN;
+            // nonlinear term X = fft(u^2 / 2) (Burger.py:487); with eddy-viscosity actions the forcing
+            // (a @ basis) * d2u/dx2 (Burger.py:445-450) is transformed in the same pass
+            Cx<T> z[P], X[P], S[P];
+            T XN, SN = T(0);
+            T left[P], right[P];
+            const bool need_nb = (flags & (F_SSM | F_DSM)) || eddy;
+            if (need_nb) halo(f, U, left, right);
 #pragma unroll
             for (int p = 0; p < P; ++p) z[p] = cx<T>(U[p].re * U[p].re, U[p].im * U[p].im);
-            f.fwd(z, X, XN, scale_nl, ws_nl);
+            if (eddy) {
+                Cx<T> zf[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    zf[p] = cx<T>(fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
+                                  fa[p].im * (U[p].re - T(2) * U[p].im + right[p]));
+                f.fwd2(z, X, XN, scale_nl, ws_nl, zf, S, SN, T(1), ws1);
+            } else {
+                f.fwd(z, X, XN, scale_nl, ws_nl);
+            }
 
             Cx<T> Fh[P];
             T FhN = T(0);
 #pragma unroll
             for (int p = 0; p < P; ++p) Fh[p] = cx<T>(0, 0);
-
-            T left[P], right[P];
-            const bool need_nb = (flags & (F_SSM | F_DSM)) || ((flags & F_ACTIONS) && !(flags & F_DFORCE));
-            if (need_nb) halo(f, U, left, right);
 
             if (flags & (F_SSM | F_DSM)) {
                 Cx<T> sgs[P], dudx[P], d2[P];
@@ -309,17 +323,17 @@ struct BurgersWarp {
                     for (int p = 0; p < P; ++p)
                         sgs[p] = cx<T>(c * fabs(dudx[p].re) * d2[p].re, c * fabs(dudx[p].im) * d2[p].im);
                 }
-                Cx<T> S[P];
-                T SN;
-                f.fwd(sgs, S, SN, T(1), ws1);
+                Cx<T> G[P];
+                T GN;
+                f.fwd(sgs, G, GN, T(1), ws1);
 #pragma unroll
-                for (int p = 0; p < P; ++p) Fh[p] = q1 ? cx<T>(r32(S[p].re), r32(S[p].im)) : S[p];
-                FhN = q1 ? r32(SN) : SN;
+                for (int p = 0; p < P; ++p) Fh[p] = q1 ? cx<T>(r32(G[p].re), r32(G[p].im)) : G[p];
+                FhN = q1 ? r32(GN) : GN;
             }
 
             if (flags & F_FORCING) {
                 // the forcing spectrum REPLACES whatever the closures accumulated (Q2)
-                if (prm.stepper > 1) {
+                if (multi_col) {
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         if (kk[p] >= 1 && kk[p] <= 3) Fc[p] = ldcx(fc_row + col * 3 + (kk[p] - 1));
@@ -331,19 +345,10 @@ struct BurgersWarp {
             }
 
             if (flags & F_ACTIONS) {
-                Cx<T> S[P];
-                T SN;
                 if (flags & F_DFORCE) {
 #pragma unroll
                     for (int p = 0; p < P; ++p) S[p] = Fa[p];
                     SN = FaN;
-                } else {
-                    // eddy-viscosity action: forcing = (a @ basis) * d2u/dx2 (Burger.py:445-450)
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        z[p] = cx<T>(fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
-                                     fa[p].im * (U[p].re - T(2) * U[p].im + right[p]));
-                    f.fwd(z, S, SN, T(1), ws1);
                 }
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -357,18 +362,18 @@ struct BurgersWarp {
             // (Burger.py:488) is a complex64 product: float32(dt) * float32(F), rounded to float32.
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                Uprev[p] = U[p];
+                if (it == nsub - 1) Uprev[p] = U[p];       // u before the last sub-step (dudt of state v1)
                 const Cx<T> fnn = cx<T>(-kw[p] * X[p].im, kw[p] * X[p].re);                // i k X
                 const Cx<T> F = q1 ? cx<T>((T)__fmul_rn(dtf, (float)Fh[p].re), (T)__fmul_rn(dtf, (float)Fh[p].im)) : Fh[p];
-                v[p] = cx<T>(fma(cF[p], F.re, fma(cfn[p], fnn.re, fma(cfo[p], fn[p].re, cv[p] * v[p].re))),
-                             fma(cF[p], F.im, fma(cfn[p], fnn.im, fma(cfo[p], fn[p].im, cv[p] * v[p].im))));
+                v[p] = cx<T>(fma(cF[p], F.re, fma(cfo[p], fma(T(-3), fnn.re, fn[p].re), cv[p] * v[p].re)),
+                             fma(cF[p], F.im, fma(cfo[p], fma(T(-3), fnn.im, fn[p].im), cv[p] * v[p].im)));
                 fn[p] = fnn;
                 bad |= blown(v[p]);
             }
             {   // k = 0: Fn = 0, F real -> Im v[0] is a constant of the motion; Nyquist: F real, Fn imaginary
                 const T fnnN = kwN * XN;
                 const T FN = q1 ? (T)__fmul_rn(dtf, (float)FhN) : FhN;
-                vN = cx<T>(fma(cFN, FN, cvN * vN.re), fma(cfnN, fnnN, fma(cfoN, fnN, cvN * vN.im)));
+                vN = cx<T>(fma(cFN, FN, cvN * vN.re), fma(cfoN, fma(T(-3), fnnN, fnN), cvN * vN.im));
                 fnN = fnnN;
                 if (f.dc) {
                     v[0].im = v0im;
@@ -387,7 +392,7 @@ struct BurgersWarp {
                 acc32[p] = __fadd_rn(acc32[p], ek_row_f32((float)v[p].re, (float)v[p].im, N, dxf));
             accN = __fadd_rn(accN, ek_row_f32((float)vN.re, (float)vN.im, N, dxf));
 
-            if (prm.hist_rows > 0) {
+            if (hist) {
                 // blow-up semantics: rows are only written while the env is healthy
                 live = live && !team_any(f, bad);
                 if (live && iout < prm.hist_rows) {
@@ -411,7 +416,7 @@ struct BurgersWarp {
                 }
             }
 
-            if (prm.reward_mode == REWARD_MSE && prm.truth) {
+            if (do_mse) {
                 // Burger.py:589-599 after every sub-step, averaged over them (burger_environment.py:153)
                 const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
                 const Cx<T>* tr = reinterpret_cast<const Cx<T>*>(prm.truth + (truth_base + row) * N);

@@ -13,8 +13,12 @@
 namespace mpde {
 
 template <typename T> int launch_burgers(const SpectralParams<T>& p, cudaStream_t st);
-template <typename T> int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st);
-template <typename T> int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_32_16(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_32_8(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_32_4(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_64_32(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_64_16(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_64_8(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_cta(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T>
 int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,

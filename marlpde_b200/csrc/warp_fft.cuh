@@ -106,6 +106,39 @@ struct WarpFFT {
         }
     }
 
+    // two independent sequences at once, interleaved stage by stage (instruction-level parallelism
+    // hides the ~37-cycle shuffle and ~13-cycle FP64 latencies)
+    __device__ __forceinline__ void fwd2(Cx<T> (&za)[P], Cx<T> (&zb)[P]) const {
+        if constexpr (P > 1) {
+#pragma unroll
+            for (int hp = P / 2; hp >= 1; hp >>= 1)
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    if ((p & hp) == 0) {
+                        const Cx<T> w = wl[P - 2 * hp + (p & (hp - 1))];
+                        const Cx<T> a = za[p], b = za[p + hp], c = zb[p], d = zb[p + hp];
+                        za[p] = a + b;
+                        zb[p] = c + d;
+                        za[p + hp] = cmul(a - b, w);
+                        zb[p + hp] = cmul(c - d, w);
+                    }
+        }
+#pragma unroll
+        for (int s = 0; s < LOGTS; ++s) {
+            const int h = TS >> (s + 1);
+            const T sg = (tl & h) ? T(-1) : T(1);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const Cx<T> oa = shfl_xor(za[p], h, tmask);
+                const Cx<T> ob = shfl_xor(zb[p], h, tmask);
+                const Cx<T> ta = cx<T>(fma(sg, za[p].re, oa.re), fma(sg, za[p].im, oa.im));
+                const Cx<T> tb = cx<T>(fma(sg, zb[p].re, ob.re), fma(sg, zb[p].im, ob.im));
+                za[p] = (h == 1) ? ta : cmul(ta, wx[s]);
+                zb[p] = (h == 1) ? tb : cmul(tb, wx[s]);
+            }
+        }
+    }
+
     // bit-reversed spectrum -> natural order, unnormalised inverse DFT (H * ifft)
     __device__ __forceinline__ void inv(Cx<T> (&z)[P]) const {
 #pragma unroll
@@ -174,6 +207,23 @@ struct RealFFT {
             X[p] = cx<T>(fma(hs, E.re, fma(ws[p].re, O.re, -ws[p].im * O.im)),
                          fma(hs, E.im, fma(ws[p].re, O.im, ws[p].im * O.re)));
             if (p == 0) nyq = (E.re - O.re) * hs;                                // k = 0: E, O real
+        }
+    }
+    // two real fields at once (see WarpFFT::fwd2)
+    __device__ __forceinline__ void fwd2(Cx<T> (&za)[P], Cx<T> (&Xa)[P], T& nyqa, T sa, const Cx<T> (&wsa)[P],
+                                         Cx<T> (&zb)[P], Cx<T> (&Xb)[P], T& nyqb, T sb, const Cx<T> (&wsb)[P]) const {
+        c.fwd2(za, zb);
+        const T ha = T(0.5) * sa, hb = T(0.5) * sb;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const Cx<T> zpa = c.mirrored(za, p), zpb = c.mirrored(zb, p);
+            const Cx<T> Ea = cx<T>(za[p].re + zpa.re, za[p].im - zpa.im), Oa = cx<T>(za[p].im + zpa.im, zpa.re - za[p].re);
+            const Cx<T> Eb = cx<T>(zb[p].re + zpb.re, zb[p].im - zpb.im), Ob = cx<T>(zb[p].im + zpb.im, zpb.re - zb[p].re);
+            Xa[p] = cx<T>(fma(ha, Ea.re, fma(wsa[p].re, Oa.re, -wsa[p].im * Oa.im)),
+                          fma(ha, Ea.im, fma(wsa[p].re, Oa.im, wsa[p].im * Oa.re)));
+            Xb[p] = cx<T>(fma(hb, Eb.re, fma(wsb[p].re, Ob.re, -wsb[p].im * Ob.im)),
+                          fma(hb, Eb.im, fma(wsb[p].re, Ob.im, wsb[p].im * Ob.re)));
+            if (p == 0) { nyqa = (Ea.re - Oa.re) * ha; nyqb = (Eb.re - Ob.re) * hb; }
         }
     }
     __device__ __forceinline__ void scaled_twiddles(T scale, Cx<T> (&ws)[P]) const {
