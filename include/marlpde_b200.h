@@ -98,6 +98,12 @@ int mpde_set_basis(mpde_env* env, int32_t M, const double* basis_host);
 /* which reward mpde_step(reward_out) evaluates (enum mpde_reward) */
 int mpde_set_reward_mode(mpde_env* env, int32_t mode);
 
+/* small per-handle switches.  MPDE_OPT_KS_UUROW (value 0/1): KS(dforce=False).step reads the float32
+ * history row uu[ioutnum], which only fou2real()/getState() refresh (KS.py:241, 316-320); 1 = the row is
+ * current for the FIRST solver step of the next mpde_step call, later rows are zero as in the reference. */
+#define MPDE_OPT_KS_UUROW 1
+int mpde_set_option(mpde_env* env, int32_t key, int64_t value);
+
 /* KS.__setup_etdrk4 tables (KS.py:127-137): HOST arrays of N doubles each, FFT order */
 int mpde_set_etdrk4(mpde_env* env, const double* E, const double* E2, const double* Q,
                     const double* f1, const double* f2, const double* f3);

@@ -7,5 +7,6 @@ environment does.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .Burger import Burger  # noqa: F401
+from .KS import KS  # noqa: F401
 
-__all__ = ["Burger"]
+__all__ = ["Burger", "KS"]

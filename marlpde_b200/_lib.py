@@ -18,6 +18,7 @@ REWARD_NONE, REWARD_SPECTRAL, REWARD_MSE, REWARD_DIRECT = 0, 1, 2, 3
 DFORCE, FORCING, SSM, DSM, IMPLICIT = 1, 2, 4, 8, 16
 (FIELD_U, FIELD_V, FIELD_FN_OLD, FIELD_U_PREV, FIELD_EK_SUM, FIELD_IOUTNUM, FIELD_T, FIELD_KPREV,
  FIELD_STATUS, FIELD_K, FIELD_NU) = range(11)
+OPT_KS_UUROW = 1
 ABI_VERSION = 1
 
 
@@ -40,6 +41,7 @@ SIGNATURES = {
     "mpde_set_nu": (C.c_int, [_vp, _dp, _i64]),
     "mpde_set_basis": (C.c_int, [_vp, _i32, _dp]),
     "mpde_set_reward_mode": (C.c_int, [_vp, _i32]),
+    "mpde_set_option": (C.c_int, [_vp, _i32, _i64]),
     "mpde_set_etdrk4": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "mpde_set_forcing": (C.c_int, [_vp, _dp, _i64]),
     "mpde_set_spectrum_ref": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),

@@ -35,6 +35,7 @@ using namespace mpde;
 struct mpde_env {
     mpde_config cfg{};
     int64_t launches = 0;
+    int aux_flags = 0;
     virtual ~mpde_env() {}
     virtual int init() = 0;
     virtual int set_nu(const double* nu, int64_t n) = 0;
@@ -293,6 +294,7 @@ struct Env : mpde_env {
             if (n_forcing == 2) flags |= F_FORCING_PER_ENV;
         }
         if (nsub == 0) flags |= F_NO_ADVANCE;
+        if (aux_flags & 1) flags |= (1 << 8);       // F_KS_UUROW
         p.flags = flags;
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
@@ -468,6 +470,14 @@ int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
 }
 int mpde_set(mpde_env* env, int32_t field, const void* src, void* stream) {
     return env && src ? env->set(field, src, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_set_option(mpde_env* env, int32_t key, int64_t value) {
+    if (!env) return fail("null argument");
+    if (key == MPDE_OPT_KS_UUROW) {
+        env->aux_flags = (env->aux_flags & ~1) | (value ? 1 : 0);
+        return 0;
+    }
+    return fail("set_option: unknown key");
 }
 int64_t mpde_launch_count(const mpde_env* env) { return env ? env->launches : -1; }
 const char* mpde_last_error(void) { return g_err.c_str(); }

@@ -24,6 +24,7 @@ template <typename T>
 int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
                             void* dst, cudaStream_t st);
 template <typename T> int launch_ks(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_ks_cta(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_fd(const SpectralParams<T>& p, int equation, bool implicit, cudaStream_t st);
 template <typename T> int launch_fd_reset(const SpectralParams<T>& p, const void* src, const uint8_t* mask, cudaStream_t st);
 template <typename T>

@@ -1,0 +1,38 @@
+// Launchers of the Kuramoto-Sivashinsky ETDRK4 step (KS.py:230-274).
+#include "dispatch.h"
+#include "ks_warp.cuh"
+
+namespace mpde {
+
+template <typename T, int N, int TS>
+__global__ void __launch_bounds__(64) ks_warp_kernel(const SpectralParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KSWarp<T, N, TS>::run(prm, reinterpret_cast<T*>(smem_raw));
+}
+
+template <typename T, int N, int TS>
+static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
+    constexpr int TPW = 32 / TS;
+    const int64_t warps = (p.B + TPW - 1) / TPW;
+    const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
+    const size_t smem = (size_t)2 * TPW * scr * sizeof(T);
+    ks_warp_kernel<T, N, TS><<<(int)((warps + 1) / 2), 64, smem, st>>>(p);
+    return 1;
+}
+
+template <typename T>
+int launch_ks(const SpectralParams<T>& p, cudaStream_t st) {
+    switch (p.N) {
+        case 8: return launch_ks_warp<T, 8, 4>(p, st);
+        case 16: return launch_ks_warp<T, 16, 8>(p, st);
+        case 32: return launch_ks_warp<T, 32, 16>(p, st);
+        case 64: return launch_ks_warp<T, 64, 32>(p, st);
+        case 128: return launch_ks_warp<T, 128, 32>(p, st);
+        default: return launch_ks_cta<T>(p, st);
+    }
+}
+
+template int launch_ks<double>(const SpectralParams<double>&, cudaStream_t);
+template int launch_ks<float>(const SpectralParams<float>&, cudaStream_t);
+
+}  // namespace mpde
