@@ -264,7 +264,7 @@ struct Env : mpde_env {
             rc = launch_fd_reset<T>(prm, src, mask, st);
         }
         if (rc > 0) { launches += rc; rc = 0; }
-        if (rc < 0) return fail("reset: unsupported N for this equation (power of two, 4..4096)");
+        if (rc < 0) return fail("reset: unsupported N for this equation (power of two, 8..2048)");
         CU(cudaGetLastError());
         return 0;
     }
@@ -310,7 +310,9 @@ struct Env : mpde_env {
                 break;
             default: rc = launch_fd<T>(p, cfg.equation, (cfg.flags & MPDE_IMPLICIT) != 0, st); break;
         }
-        if (rc < 0) return fail("step: unsupported N for this equation");
+        if (rc == -2) return fail("step: the Smagorinsky closures are only available for N <= 256");
+        if (rc == -3) return fail("step: the MSE reward is only available for N <= 256");
+        if (rc < 0) return fail("step: unsupported N for this equation (power of two, 8..2048)");
         launches += rc;
         CU(cudaGetLastError());
         return 0;
@@ -401,9 +403,10 @@ int mpde_create(const mpde_config* cfg, mpde_env** out) {
     if (cfg->struct_size != (int32_t)sizeof(mpde_config)) return fail("create: mpde_config size mismatch (ABI)");
     if (cfg->nenvs <= 0) return fail("create: nenvs must be positive");
     if (cfg->N < 4) return fail("create: N must be >= 4");
+    if ((cfg->equation == MPDE_BURGERS || cfg->equation == MPDE_KS) && cfg->N < 8) return fail("create: spectral solvers need N >= 8");
     const bool spectral = cfg->equation == MPDE_BURGERS || cfg->equation == MPDE_KS;
     if (spectral && !is_pow2(cfg->N)) return fail("create: spectral solvers need a power-of-two N");
-    if (spectral && cfg->N > 4096) return fail("create: N > 4096 not supported");
+    if (spectral && cfg->N > 2048) return fail("create: N > 2048 not supported");
     if (cfg->num_agents < 1 || cfg->N % cfg->num_agents) return fail("create: num_agents must divide N");
     if (cfg->stepper < 1) return fail("create: stepper must be >= 1");
     if ((cfg->flags & MPDE_SSM) && (cfg->flags & MPDE_DSM)) return fail("create: ssm and dsm are exclusive (Burger.py:50)");
