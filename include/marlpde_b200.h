@@ -57,7 +57,8 @@ enum mpde_field {
     MPDE_FIELD_KPREV = 7,   /* [B] real        kPrevRelErr of the spectral reward                        */
     MPDE_FIELD_STATUS = 8,  /* [B] int32                                                                 */
     MPDE_FIELD_K = 9,       /* [N] real        wavenumber table (Burger.k)                               */
-    MPDE_FIELD_NU = 10      /* [B] real                                                                  */
+    MPDE_FIELD_NU = 10,     /* [B] real                                                                  */
+    MPDE_FIELD_ALPHA = 11   /* [B] real        Advection Courant number nu*dt/dx (Advection.py:43)        */
 };
 
 typedef struct mpde_config {
@@ -102,6 +103,11 @@ int mpde_set_reward_mode(mpde_env* env, int32_t mode);
  * history row uu[ioutnum], which only fou2real()/getState() refresh (KS.py:241, 316-320); 1 = the row is
  * current for the FIRST solver step of the next mpde_step call, later rows are zero as in the reference. */
 #define MPDE_OPT_KS_UUROW 1
+/* MPDE_OPT_NUM_AGENTS: numAgents of the NEXT calls (Diffusion/Advection pass it per call: step(actions, numAgents),
+ * getState(numAgents), getMseReward(numAgents)).  MPDE_OPT_NUM_ACTIONS: actions per environment of the FD solvers
+ * (Diffusion: 1 or N, Advection: 2 or 2N). */
+#define MPDE_OPT_NUM_AGENTS 2
+#define MPDE_OPT_NUM_ACTIONS 3
 int mpde_set_option(mpde_env* env, int32_t key, int64_t value);
 
 /* KS.__setup_etdrk4 tables (KS.py:127-137): HOST arrays of N doubles each, FFT order */

@@ -8,5 +8,6 @@ environment does.  There is no CPU fallback.
 from . import _lib  # noqa: F401
 from .Burger import Burger  # noqa: F401
 from .KS import KS  # noqa: F401
+from ._fd import Diffusion, Advection  # noqa: F401
 
-__all__ = ["Burger", "KS"]
+__all__ = ["Burger", "KS", "Diffusion", "Advection"]

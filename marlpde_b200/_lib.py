@@ -17,8 +17,8 @@ RUNNING, TRUNCATED = 0, 1
 REWARD_NONE, REWARD_SPECTRAL, REWARD_MSE, REWARD_DIRECT = 0, 1, 2, 3
 DFORCE, FORCING, SSM, DSM, IMPLICIT = 1, 2, 4, 8, 16
 (FIELD_U, FIELD_V, FIELD_FN_OLD, FIELD_U_PREV, FIELD_EK_SUM, FIELD_IOUTNUM, FIELD_T, FIELD_KPREV,
- FIELD_STATUS, FIELD_K, FIELD_NU) = range(11)
-OPT_KS_UUROW = 1
+ FIELD_STATUS, FIELD_K, FIELD_NU, FIELD_ALPHA) = range(12)
+OPT_KS_UUROW, OPT_NUM_AGENTS, OPT_NUM_ACTIONS = 1, 2, 3
 ABI_VERSION = 1
 
 

@@ -158,6 +158,11 @@ struct Env : mpde_env {
             if (dalloc(&etd, (size_t)6 * N)) return -1;
             prm.etd = etd;
         }
+        if (cfg.equation == MPDE_ADVECTION) {      // Courant number alpha[B] (Advection.py:43) lives in the etd slot
+            T* al;
+            if (dalloc(&al, B)) return -1;
+            prm.etd = al;
+        }
         return 0;
     }
 
@@ -165,6 +170,11 @@ struct Env : mpde_env {
         if (n != 1 && n != cfg.nenvs) return fail("set_nu: n must be 1 or nenvs");
         std::vector<T> h(cfg.nenvs);
         for (int64_t i = 0; i < cfg.nenvs; ++i) h[i] = (T)nu[n == 1 ? 0 : i];
+        if (cfg.equation == MPDE_ADVECTION) {      // alpha = nu dt / dx (Advection.py:43)
+            std::vector<T> al(cfg.nenvs);
+            for (int64_t i = 0; i < cfg.nenvs; ++i) al[i] = (T)(nu[n == 1 ? 0 : i] * cfg.dt / (cfg.L / cfg.N));
+            if (upload(const_cast<T*>(prm.etd), al)) return -1;
+        }
         return upload(const_cast<T*>(prm.nu), h);
     }
 
@@ -283,9 +293,13 @@ struct Env : mpde_env {
         if (cfg.flags & MPDE_FORCING) flags |= F_FORCING;
         if (cfg.flags & MPDE_SSM) flags |= F_SSM;
         if (cfg.flags & MPDE_DSM) flags |= F_DSM;
+        p.A = cfg.num_agents;
+        p.M = cfg.M;
         if (actions) {
-            if (cfg.M <= 0) return fail("step: actions given but M == 0 (call setup_basis first)");
+            if (cfg.M <= 0) return fail("step: actions given but M == 0 (call setup_basis / set M first)");
             if (spectral() && !basis_set) return fail("step: actions given but no basis was set");
+            if (cfg.equation == MPDE_DIFFUSION && cfg.M != 1 && cfg.M != cfg.N) return fail("step: Diffusion takes 1 or N actions");
+            if (cfg.equation == MPDE_ADVECTION && cfg.M != 2 && cfg.M != 2 * cfg.N) return fail("step: Advection takes 2 or 2N actions");
             flags |= F_ACTIONS;
             if (basis_dense) flags |= F_BASIS_DENSE;
         }
@@ -298,7 +312,7 @@ struct Env : mpde_env {
         p.flags = flags;
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
-            if (cfg.reward_mode == MPDE_REWARD_MSE && !p.truth && cfg.equation == MPDE_BURGERS)
+            if (cfg.reward_mode == MPDE_REWARD_MSE && !p.truth)
                 return fail("step: MSE reward without mpde_set_truth");
         }
         int rc;
@@ -358,6 +372,9 @@ struct Env : mpde_env {
                 if (!spectral()) return fail("get: field only exists for spectral solvers");
                 return copy(prm.kwave, sizeof(T) * N);
             case MPDE_FIELD_NU: return copy(prm.nu, sizeof(T) * B);
+            case MPDE_FIELD_ALPHA:
+                if (cfg.equation != MPDE_ADVECTION) return fail("get: field only exists for Advection");
+                return copy(prm.etd, sizeof(T) * B);
         }
         return fail("get: unknown field");
     }
@@ -391,6 +408,9 @@ struct Env : mpde_env {
             case MPDE_FIELD_KPREV: return copy(prm.kprev, sizeof(T) * B);
             case MPDE_FIELD_STATUS: return copy(prm.status, sizeof(int) * B);
             case MPDE_FIELD_NU: return copy(const_cast<T*>(prm.nu), sizeof(T) * B);
+            case MPDE_FIELD_ALPHA:
+                if (cfg.equation != MPDE_ADVECTION) return fail("set: field only exists for Advection");
+                return copy(const_cast<T*>(prm.etd), sizeof(T) * B);
         }
         return fail("set: field is read-only or unknown");
     }
@@ -478,6 +498,17 @@ int mpde_set_option(mpde_env* env, int32_t key, int64_t value) {
     if (!env) return fail("null argument");
     if (key == MPDE_OPT_KS_UUROW) {
         env->aux_flags = (env->aux_flags & ~1) | (value ? 1 : 0);
+        return 0;
+    }
+    if (key == MPDE_OPT_NUM_AGENTS) {
+        if (value < 1 || env->cfg.N % value) return fail("set_option: num_agents must divide N");
+        env->cfg.num_agents = (int32_t)value;
+        return 0;
+    }
+    if (key == MPDE_OPT_NUM_ACTIONS) {
+        if (env->cfg.equation == MPDE_BURGERS || env->cfg.equation == MPDE_KS)
+            return fail("set_option: spectral solvers set M through mpde_set_basis");
+        env->cfg.M = (int32_t)value;
         return 0;
     }
     return fail("set_option: unknown key");

@@ -1,0 +1,97 @@
+"""GPU parity of the Diffusion / Advection stencil environments against golden vectors recorded
+from the reference classes (actions as stencil weights, per-agent windows, MSE / direct rewards,
+analytic solutions, implicit Euler)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+DIFF = {"plain": ("sinus", 1), "lap": ("sinus", 1), "point_A1": ("box", 1), "point_A4": ("gaussian", 4),
+        "point_AN": ("sinus", 32), "implicit": ("box", 1)}
+
+
+@pytest.mark.parametrize("tag", sorted(DIFF))
+def test_diffusion(golden, tag):
+    from marlpde_b200 import Diffusion
+    g = golden("fd.npz")
+    p = f"diff_{tag}/"
+    N, L, dt, nu, A = g[p + "cfg"]
+    N, A = int(N), int(A)
+    case = DIFF[tag][0]
+    U, acts, S = g[p + "u"], g[p + "actions"], g[p + "states"]
+    d = Diffusion(L=L, N=N, dt=dt, nu=nu, nsteps=30, case=case, implicit=(tag == "implicit"))
+    assert rel(d.u, U[0]) < 1e-15
+    assert rel(np.array(d.getState(A)).reshape(-1), S[0].reshape(-1)) < 1e-15
+    for i in range(len(U) - 1):
+        if len(acts):
+            a = acts[i]
+            d.step(a.tolist() if A == 1 else a.reshape(A, -1).tolist(), numAgents=A)
+        else:
+            d.step()
+        assert rel(d.u, U[i + 1]) < 1e-12, (tag, i)
+        assert rel(np.array(d.getState(A)).reshape(-1), S[i + 1].reshape(-1)) < 1e-12
+        if len(g[p + "mse"]):
+            np.testing.assert_allclose(np.atleast_1d(d.getMseReward(A)), g[p + "mse"][i], rtol=1e-8, atol=1e-30)
+        if len(g[p + "direct"]):
+            np.testing.assert_allclose(d.getDirectReward(A), g[p + "direct"][i], rtol=1e-8, atol=1e-15)
+    assert rel(d.uu, U) < 1e-12
+    if case == "sinus":
+        assert rel(d.solution, g[p + "solution"]) < 1e-14
+
+
+@pytest.mark.parametrize("tag,A", [("lax", 1), ("global", 1), ("point_A1", 1), ("point_A4", 4)])
+def test_advection(golden, tag, A):
+    from marlpde_b200 import Advection
+    g = golden("fd.npz")
+    p = f"adv_{tag}/"
+    N, L, dt, nu, _ = g[p + "cfg"]
+    N = int(N)
+    U, acts, S = g[p + "u"], g[p + "actions"], g[p + "states"]
+    a_ = Advection(L=L, N=N, dt=dt, nu=nu, nsteps=30, case="sinus")
+    for i in range(len(U) - 1):
+        if len(acts):
+            a = acts[i]
+            a_.step(a.tolist() if A == 1 else a.reshape(A, -1).tolist(), numAgents=A)
+        else:
+            a_.step()
+        assert rel(a_.u, U[i + 1]) < 1e-12, (tag, i)
+        assert rel(np.array(a_.getState(A)).reshape(-1), S[i + 1].reshape(-1)) < 1e-12
+        np.testing.assert_allclose(np.atleast_1d(a_.getMseReward(A)), g[p + "mse"][i], rtol=1e-8, atol=1e-30)
+    assert rel(a_.solution, g[p + "solution"]) < 1e-14
+
+
+def test_known_answers_and_batching():
+    """Action -2 == standard Laplacian; Lax weights == FDstep; batch rows == single envs (bitwise);
+    convergence to the analytic sinus solutions."""
+    from marlpde_b200 import Diffusion, Advection
+    N, L = 64, 2 * np.pi
+    d0 = Diffusion(L=L, N=N, dt=1e-3, nu=0.1, nsteps=200, case="sinus")
+    d1 = Diffusion(L=L, N=N, dt=1e-3, nu=0.1, nsteps=200, case="sinus")
+    d0.simulate()
+    for _ in range(200):
+        d1.step([-2.0])
+    assert rel(d0.u, d1.u.cpu().numpy()) < 1e-13
+    assert rel(d0.u, d0.getAnalyticalSolution(d0.t)) < 1e-3
+    offs = np.array([0.0, 0.3, -0.2, 0.1, 0.7])
+    db = Diffusion(L=L, N=N, dt=1e-3, nu=0.1, nsteps=50, case="sinus", nenvs=5, offset=offs)
+    acts = -2.0 + 0.1 * np.random.default_rng(0).normal(size=(5, N))
+    db.step_n(acts, 1, 50)
+    for e in (0, 2, 4):
+        d = Diffusion(L=L, N=N, dt=1e-3, nu=0.1, nsteps=50, case="sinus", offset=offs[e])
+        d.step_n(acts[e], 1, 50)
+        assert torch.equal(d.u, db.u[e])
+    a0 = Advection(L=L, N=N, dt=0.09, nu=1.0, nsteps=20, case="sinus")
+    a1 = Advection(L=L, N=N, dt=0.09, nu=1.0, nsteps=20, case="sinus")
+    al = a0.alpha
+    a0.simulate()
+    for _ in range(20):
+        a1.step([0.5 + 0.5 * al, 0.5 - 0.5 * al])
+    assert rel(a0.u, a1.u.cpu().numpy()) < 1e-13
+    assert rel(a0.u, a0.getAnalyticalSolution(a0.t)) < 2e-2
