@@ -191,19 +191,33 @@ def gpu_arm(args):
     acts_host = torch.from_numpy(np.repeat(rng.uniform(0.05, 0.1, (pool, B_PER_GPU, 1)), M, axis=2).copy()).pin_memory()
     acts = acts_host.to(device)
     S = envs[0]._state_size
+    flats, gflats, works = [], [], [None] * pool
     if world > 1:
-        g_state = torch.empty((world * B_PER_GPU, S), device=device, dtype=torch.float64)
-        g_reward = torch.empty((world * B_PER_GPU, 1), device=device, dtype=torch.float64)
+        # each batch writes state + reward into ONE flat send buffer -> a single all-gather per RL step,
+        # issued asynchronously on NCCL's stream so it overlaps the next batch's kernel
+        for env in envs:
+            fl = torch.zeros(B_PER_GPU * (S + 1), device=device, dtype=torch.float64)
+            env.bind_output(fl[:B_PER_GPU * S].view(B_PER_GPU, S), fl[B_PER_GPU * S:].view(B_PER_GPU, 1))
+            flats.append(fl)
+            gflats.append(torch.zeros(world * B_PER_GPU * (S + 1), device=device, dtype=torch.float64))
 
     def one_step(i):
-        env = envs[i % pool]
-        st, rw = env.step_n(acts[i % pool], NSUB)
+        k = i % pool
+        if world > 1 and works[k] is not None:
+            works[k].wait()                 # the send buffer of this batch is about to be overwritten
+        st, rw = envs[k].step_n(acts[k], NSUB)
         if world > 1:      # learner-side gather of per-env summaries (north_star: the only collective)
-            dist.all_gather_into_tensor(g_state, st)
-            dist.all_gather_into_tensor(g_reward, rw)
+            works[k] = dist.all_gather_into_tensor(gflats[k], flats[k], async_op=True)
         return st, rw
 
+    def drain():
+        for k in range(pool):
+            if works[k] is not None:
+                works[k].wait()
+                works[k] = None
+
     def sync():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -217,6 +231,7 @@ def gpu_arm(args):
     ev0.record()
     for i in range(K):
         one_step(W + i)
+    drain()
     ev1.record()
     sync()
     ms = ev0.elapsed_time(ev1)
@@ -234,8 +249,7 @@ def gpu_arm(args):
         a_dev.copy_(acts_host[i % pool], non_blocking=True)               # H2D of this step's actions
         st, rw = env.step_n(a_dev, NSUB)
         if world > 1:
-            dist.all_gather_into_tensor(g_state, st)
-            dist.all_gather_into_tensor(g_reward, rw)
+            dist.all_gather_into_tensor(gflats[i % pool], flats[i % pool])
         st_host.copy_(st, non_blocking=True)                              # D2H of state + reward
         rw_host.copy_(rw, non_blocking=True)
         torch.cuda.synchronize()                                          # the learner needs them before acting

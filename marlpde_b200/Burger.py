@@ -257,6 +257,14 @@ class Burger(SpectralEnv):
         assert a.shape[1] == self.M, "[Burger] Wrong number of actions (provided {}/{}".format(a.shape[1], self.M)
         return a.contiguous()
 
+    def bind_output(self, state_buf, reward_buf):
+        """Let the caller own the [B,S] state and [B,A] reward buffers step_n writes (e.g. two views of
+        one flat tensor that is all-gathered to the learner in a single collective)."""
+        assert state_buf.shape == self._state_buf.shape and reward_buf.shape == self._reward_buf.shape
+        assert state_buf.is_contiguous() and reward_buf.is_contiguous()
+        self._state_buf, self._reward_buf = state_buf, reward_buf
+        self._state_at = self._reward_at = -1
+
     def step_n(self, actions=None, n=1, want_state=True, want_reward=True):
         """``n`` solver steps with the same actions (the inner loop of
         burger_environment.py:148-155) + getState + reward, as ONE kernel launch.

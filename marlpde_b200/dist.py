@@ -61,7 +61,8 @@ class ShardedBatch:
 
     ``factory(n_local, ids)`` builds this rank's environments from the GLOBAL ids it owns, e.g.
     ``lambda n, ids: Burger(N=32, seed=42 + ids, nenvs=n, ...)``.  ``step_n`` advances the local shard
-    with one kernel launch and all-gathers state and reward for the learner.
+    with one kernel launch; the kernel writes state and reward into ONE flat send buffer, which a
+    single all-gather delivers to every rank (the learner reads ``states`` / ``rewards`` views).
     """
 
     def __init__(self, n_global, factory):
@@ -70,16 +71,48 @@ class ShardedBatch:
         self.lo, self.hi = shard_range(self.n_global, self.rank, self.world_size)
         self.ids = np.arange(self.lo, self.hi)
         self.env = factory(self.hi - self.lo, self.ids)
+        self._flat = self._gflat = None
+        if hasattr(self.env, "bind_output"):
+            nl = self.hi - self.lo
+            S, A = self.env._state_buf.shape[1], self.env._reward_buf.shape[1]
+            self._S, self._A = S, A
+            buf = self.env._state_buf
+            self._flat = torch.zeros(nl * (S + A), dtype=buf.dtype, device=buf.device)
+            self.env.bind_output(self._flat[:nl * S].view(nl, S), self._flat[nl * S:].view(nl, A))
+            self._gflat = torch.zeros((self.world_size, nl * (S + A)), dtype=buf.dtype, device=buf.device)
         self._g_state = self._g_reward = None
+        self._work = None
 
     def local(self, per_env):
         return shard(per_env, self.n_global, self.rank, self.world_size)
 
-    def step_n(self, actions_global_or_local, n=1, **kw):
+    def wait(self):
+        """Block the current stream until the last asynchronous gather has landed."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+
+    def views(self):
+        """(states [R, B/R, S], rewards [R, B/R, A]) views of the gathered buffer, global env order."""
+        nl = self.hi - self.lo
+        g = self._gflat
+        return g[:, :nl * self._S].view(self.world_size, nl, self._S), g[:, nl * self._S:].view(self.world_size, nl, self._A)
+
+    def step_n(self, actions_global_or_local, n=1, async_gather=False, **kw):
         a = actions_global_or_local
         if a is not None and len(a) == self.n_global and self.world_size > 1:
             a = a[self.lo:self.hi]
+        self.wait()                                   # the send buffer is about to be overwritten
         st, rw = self.env.step_n(a, n, **kw)
+        if self._flat is not None and st is not None and rw is not None:
+            if self.world_size == 1:
+                self._gflat[0].copy_(self._flat)
+            else:
+                self._work = dist.all_gather_into_tensor(self._gflat.view(-1), self._flat, async_op=True)
+                if not async_gather:
+                    self.wait()
+            gs, gr = self.views()
+            return gs.reshape(self.n_global, self._S), gr.reshape(self.n_global, self._A)
         gs = gr = None
         if st is not None:
             if self._g_state is None or self._g_state.shape[1:] != st.shape[1:]:
