@@ -239,27 +239,36 @@ def gpu_arm(args):
     alive = all(int((e.status != 0).sum()) == 0 for e in envs)
 
     # ---- end to end through the public API with HOST buffers --------------------------------
-    st_host = torch.empty((B_PER_GPU, S), dtype=torch.float64).pin_memory()
-    rw_host = torch.empty((B_PER_GPU, 1), dtype=torch.float64).pin_memory()
-    a_dev = torch.empty((B_PER_GPU, M), device=device, dtype=torch.float64)
-    Ke = max(10, min(K, 1000))
+    # Every RL step of every batch: pinned-host actions -> H2D -> step_n (one launch) -> D2H of state and
+    # reward -> the host waits for them before that batch gets its next actions.  The learner keeps
+    # `depth` independent batches in flight (marlpde_b200.pipeline.HostPipeline) so PCIe transfers of one
+    # batch overlap the kernel of another; each batch's own action->state chain stays strictly serial.
+    from marlpde_b200.pipeline import HostPipeline
+    depth = min(pool, max(1, args.depth))
+    drain()
 
-    def e2e_step(i):
-        env = envs[i % pool]
-        a_dev.copy_(acts_host[i % pool], non_blocking=True)               # H2D of this step's actions
-        st, rw = env.step_n(a_dev, NSUB)
-        if world > 1:
-            dist.all_gather_into_tensor(gflats[i % pool], flats[i % pool])
-        st_host.copy_(st, non_blocking=True)                              # D2H of state + reward
-        rw_host.copy_(rw, non_blocking=True)
-        torch.cuda.synchronize()                                          # the learner needs them before acting
+    def gather(k, st, rw):            # N > 1: the learner-side all-gather stays part of every step
+        dist.all_gather_into_tensor(gflats[k], flats[k])
 
-    for i in range(3):
-        e2e_step(i)
+    pipe = HostPipeline(envs[:depth], NSUB, post_step=gather if world > 1 else None)
+    for k in range(depth):
+        pipe.act_host[k].copy_(acts_host[k])
+    Ke = max(depth, min(K, 2000))
+    checksum = 0.0
+
+    def e2e_round(n):
+        nonlocal checksum
+        for i in range(n):
+            k = i % depth
+            st_h, rw_h = pipe.collect(k)              # results of this batch's previous step are on the host
+            checksum += float(rw_h[0, 0])             # the host really reads them
+            pipe.submit(k)                            # next actions for this batch (already in pinned memory)
+        pipe.drain()
+
+    e2e_round(3 * depth)
     sync()
     t0 = time.perf_counter()
-    for i in range(Ke):
-        e2e_step(3 + i)
+    e2e_round(Ke)
     sync()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
@@ -283,8 +292,10 @@ def gpu_arm(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": B_PER_GPU * M * 8, "d2h_bytes_per_step": B_PER_GPU * (S + 1) * 8,
-                    "steps": Ke, "note": "pinned host actions -> H2D -> step_n -> D2H state+reward -> sync, per RL step"},
+                    "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                    "steps": Ke, "batches_in_flight": depth,
+                    "note": "per RL step of a batch: pinned host actions -> H2D -> step_n -> D2H state+reward -> host waits; "
+                            "independent batches overlap (HostPipeline)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -311,6 +322,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--depth", type=int, default=4, help="e2e: independent batches in flight")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -147,6 +147,14 @@ int mpde_reset_v(mpde_env* env, const void* v0_dev, const uint8_t* mask_dev, voi
  * status is kept in the library (MPDE_FIELD_STATUS). */
 int mpde_step(mpde_env* env, const void* actions_dev, int32_t nsub, void* state_out, void* reward_out, void* stream);
 
+/* Same as mpde_step for a HOST-side caller: `actions_host`, `state_host`, `reward_host` are (preferably
+ * pinned) host buffers; the library stages them through device buffers it owns and enqueues
+ * H2D copy -> step kernel -> D2H copies on `stream`, returning immediately.  The results are valid once the
+ * stream (or an event recorded after the call) has completed.  This is the call the reference's environment
+ * loop maps to when the policy lives on the host (burger_environment.py:140-190: s["Action"] in, s["State"] /
+ * s["Reward"] out). */
+int mpde_step_host(mpde_env* env, const void* actions_host, int32_t nsub, void* state_host, void* reward_host, void* stream);
+
 /* attribute access (u, v, Fn_old, ioutnum, t, ...): DEVICE destination / source of the natural shape */
 int mpde_get(mpde_env* env, int32_t field, void* dst_dev, void* stream);
 int mpde_set(mpde_env* env, int32_t field, const void* src_dev, void* stream);

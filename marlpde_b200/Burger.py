@@ -284,6 +284,25 @@ class Burger(SpectralEnv):
             self._reward_at = self.ioutnum
         return st, rw
 
+    def step_n_host(self, actions_host, n, state_host, reward_host=None, stream=None):
+        """Host-buffer form of step_n for a host-side policy: (pinned) host actions [B,M] in, (pinned) host
+        state [B,S] / reward [B,A] out, everything enqueued asynchronously on ``stream`` (default: the current
+        stream) by ONE library call (H2D copy -> step kernel -> D2H copies).  Results are valid after the
+        stream / an event recorded behind this call completes."""
+        self._upload_forcing()
+        for t_ in (actions_host, state_host, reward_host):
+            assert t_ is None or (not t_.is_cuda and t_.is_contiguous() and t_.dtype == self.dtype)
+        st = stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        have_rw = reward_host is not None and (self._spec_ref is not None or self._truth_shift is not None)
+        L_check(self._lib.mpde_step_host(self._h, actions_host.data_ptr() if actions_host is not None else None, int(n),
+                                         state_host.data_ptr() if state_host is not None else None,
+                                         reward_host.data_ptr() if have_rw else None, st))
+        self.stepnum += n
+        self.ioutnum += n
+        for _ in range(n):
+            self.t += self.dt
+        self._state_at = self._reward_at = -1
+
     def step(self, actions=None):
         """Burger.py:333-499: one solver step."""
         self.step_n(actions, 1, want_state=False, want_reward=self._truth_shift is not None)

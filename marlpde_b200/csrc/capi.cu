@@ -47,6 +47,7 @@ struct mpde_env {
     virtual int set_history(void* uu, void* vv, double* ektt, int64_t rows) = 0;
     virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
+    virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -332,6 +333,24 @@ struct Env : mpde_env {
         return 0;
     }
 
+    // host-buffer variant: stage through library-owned device buffers (allocated on first use)
+    T *stage_act = nullptr, *stage_state = nullptr, *stage_reward = nullptr;
+    size_t stage_act_n = 0, stage_state_n = 0, stage_reward_n = 0;
+    int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        const size_t B = (size_t)cfg.nenvs;
+        const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
+        const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
+        if (na > stage_act_n) { if (dalloc(&stage_act, na)) return -1; stage_act_n = na; }
+        if (ns > stage_state_n) { if (dalloc(&stage_state, ns)) return -1; stage_state_n = ns; }
+        if (nr > stage_reward_n) { if (dalloc(&stage_reward, nr)) return -1; stage_reward_n = nr; }
+        if (na) CU(cudaMemcpyAsync(stage_act, actions, na * sizeof(T), cudaMemcpyHostToDevice, st));
+        if (step(na ? stage_act : nullptr, nsub, ns ? stage_state : nullptr, nr ? stage_reward : nullptr, st)) return -1;
+        if (ns) CU(cudaMemcpyAsync(state_out, stage_state, ns * sizeof(T), cudaMemcpyDeviceToHost, st));
+        if (nr) CU(cudaMemcpyAsync(reward_out, stage_reward, nr * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+
     int get(int field, void* dst, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
         const int64_t B = cfg.nenvs;
@@ -487,6 +506,9 @@ int mpde_reset_v(mpde_env* env, const void* v0, const uint8_t* mask, void* strea
 }
 int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_step_host(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
+    return env ? env->step_host(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");

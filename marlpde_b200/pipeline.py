@@ -1,0 +1,60 @@
+"""Host <-> device pipelining for a learner that keeps several independent environment batches in
+flight (the usual asynchronous vectorised-environment pattern).
+
+Each slot owns one environment batch, one CUDA stream and pinned host buffers.  ``submit(k, actions)``
+enqueues, on slot k's stream: H2D copy of the actions -> ``step_n`` (one kernel launch) -> D2H copies of
+state and reward; ``collect(k)`` waits for that slot only.  While slot k's results travel back over PCIe,
+slot k+1's kernel runs and slot k+2's actions travel in -- every batch still sees its own strictly serial
+action -> step -> state chain.
+"""
+import torch
+
+
+class HostPipeline:
+    def __init__(self, envs, n_sub, post_step=None):
+        self.envs, self.n_sub = list(envs), int(n_sub)
+        self.post_step = post_step          # e.g. the all-gather to the learner rank, enqueued after the step
+        e0 = self.envs[0]
+        dev, dt = e0.device, e0.dtype
+        B, M, S, A = e0.nenvs, e0.M, e0._state_buf.shape[1], e0._reward_buf.shape[1]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.envs]
+        self.done = [torch.cuda.Event() for _ in self.envs]
+        self.act_host = [torch.empty((B, M), dtype=dt).pin_memory() for _ in self.envs]
+        self.act_dev = [torch.empty((B, M), dtype=dt, device=dev) for _ in self.envs]
+        self.state_host = [torch.empty((B, S), dtype=dt).pin_memory() for _ in self.envs]
+        self.reward_host = [torch.empty((B, A), dtype=dt).pin_memory() for _ in self.envs]
+        self.h2d_bytes = self.act_host[0].numel() * self.act_host[0].element_size()
+        self.d2h_bytes = (self.state_host[0].numel() + self.reward_host[0].numel()) * self.state_host[0].element_size()
+        self.pending = [False] * len(self.envs)
+
+    def submit(self, k, actions_host=None):
+        """Start one RL step of batch k with the host-side ``actions`` ([B,M]; None = reuse the pinned buffer)."""
+        if actions_host is not None:
+            self.act_host[k].copy_(torch.as_tensor(actions_host))
+        if self.post_step is None and hasattr(self.envs[k], "step_n_host"):
+            # one library call enqueues H2D -> kernel -> D2H on this slot's stream
+            self.envs[k].step_n_host(self.act_host[k], self.n_sub, self.state_host[k], self.reward_host[k],
+                                     stream=self.streams[k])
+            self.done[k].record(self.streams[k])
+        else:
+            with torch.cuda.stream(self.streams[k]):
+                self.act_dev[k].copy_(self.act_host[k], non_blocking=True)
+                st, rw = self.envs[k].step_n(self.act_dev[k], self.n_sub)
+                if self.post_step is not None:
+                    self.post_step(k, st, rw)
+                self.state_host[k].copy_(st, non_blocking=True)
+                if rw is not None:
+                    self.reward_host[k].copy_(rw, non_blocking=True)
+                self.done[k].record(self.streams[k])
+        self.pending[k] = True
+
+    def collect(self, k):
+        """Wait for batch k's step; returns (state [B,S], reward [B,A]) pinned host tensors."""
+        if self.pending[k]:
+            self.done[k].synchronize()
+            self.pending[k] = False
+        return self.state_host[k], self.reward_host[k]
+
+    def drain(self):
+        for k in range(len(self.envs)):
+            self.collect(k)

@@ -224,3 +224,28 @@ def test_full_size_config2_properties():
     from marlpde_b200 import _lib as LB
     kprev = env._get(LB.FIELD_KPREV, (B,), torch.float64)
     assert torch.allclose(tot[:, 0], -kprev, rtol=1e-9, atol=1e-12)
+
+
+def test_host_buffer_step_equals_device_step(golden):
+    """mpde_step_host (pinned host in/out through HostPipeline) == the device-pointer path, bitwise."""
+    from marlpde_b200.pipeline import HostPipeline
+    g = golden("burger_steps.npz")
+    V, A = g["eddy_forced/v"], g["eddy_forced/actions"]
+    rows = [0, 5, 11, 17]
+    ref_env, _ = make_env("eddy_forced", g, B=4, history=False)
+    ref_env.IC(v0=V[rows])
+    ref_env.set_spectrum_reference(np.abs(np.random.default_rng(0).normal(1, 0.1, (61, 16))) + 0.1)
+    envs = []
+    for _ in range(2):
+        e, _m = make_env("eddy_forced", g, B=4, history=False)
+        e.IC(v0=V[rows])
+        e.set_spectrum_reference(np.abs(np.random.default_rng(0).normal(1, 0.1, (61, 16))) + 0.1)
+        envs.append(e)
+    pipe = HostPipeline(envs, 10)
+    for k in range(2):
+        pipe.submit(k, A[[0, 1, 2, 3]])
+    st_ref, rw_ref = ref_env.step_n(A[[0, 1, 2, 3]], 10)
+    for k in range(2):
+        st, rw = pipe.collect(k)
+        assert torch.equal(st, st_ref.cpu()) and torch.equal(rw, rw_ref.cpu())
+    assert torch.equal(envs[1].v, ref_env.v)
