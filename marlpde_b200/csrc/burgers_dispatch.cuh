@@ -12,8 +12,9 @@ constexpr int min_blocks() {
     return (sizeof(T) == 8 ? (P <= 1 ? 8 : (P <= 2 ? 6 : 4)) : (P <= 2 ? 8 : 4));
 }
 
+// 256 threads x (min_blocks / 4) CTAs give the same register budget as 64 x min_blocks
 template <typename T, int N, int TS, int SF, bool LEAN>
-__global__ void __launch_bounds__(64, (min_blocks<T, N, TS>())) burgers_warp_kernel(const SpectralParams<T> prm) {
+__global__ void __launch_bounds__(256, (min_blocks<T, N, TS>() / 4 > 0 ? min_blocks<T, N, TS>() / 4 : 1)) burgers_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BurgersWarp<T, N, TS, SF, LEAN>::run(prm, reinterpret_cast<T*>(smem_raw));
 }
@@ -22,10 +23,15 @@ template <typename T, int N, int TS, int SF, bool LEAN = false>
 int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
     constexpr int TPW = 32 / TS;
     const int64_t warps = (p.B + TPW - 1) / TPW;
-    const int block = 64;
-    const int grid = (int)((warps + 1) / 2);
+    int wpc = 2;                                   // warps per CTA (MPDE_WPC = 1, 2, 4, 8 overrides: tuning)
+    if (const char* s = std::getenv("MPDE_WPC")) {
+        const int v = std::atoi(s);
+        if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
+    }
+    const int block = 32 * wpc;
+    const int grid = (int)((warps + wpc - 1) / wpc);
     const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
-    const size_t smem = (size_t)2 * TPW * scr * sizeof(T);
+    const size_t smem = (size_t)wpc * TPW * scr * sizeof(T);
     burgers_warp_kernel<T, N, TS, SF, LEAN><<<grid, block, smem, st>>>(p);
     return 1;
 }

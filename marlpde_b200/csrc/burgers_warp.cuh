@@ -93,25 +93,62 @@ struct BurgersWarp {
         const int scr = max(prm.M, 2 * N + N / 2);
         T* scratch = smem + (size_t)(warp * TPW + team) * scr;
 
+        // ---- issue every global load of the prologue up front (one memory round trip) ---------------
+        int kk[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) kk[p] = f.k(p);
+        const bool was_live = has && prm.status[ec] == 0;
+        bool live = was_live;
+        int iout = prm.iout[ec];
+        T tnow = prm.tnow[ec];
+        const T nu = prm.nu[ec];
+        Cx<T> v[P], fn[P];
+        T kw[P];
+        float acc32[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            v[p] = ldcx(prm.v + ec * NH + kk[p]);
+            fn[p] = ldcx(prm.fn + ec * NH + kk[p]);
+            kw[p] = prm.kwave[kk[p]];
+            acc32[p] = prm.acc[ec * NH + kk[p]];
+        }
+        // Nyquist mode: complex in the reference when the IC came from a truncated DNS spectrum
+        // (quirk Q5); its imaginary part and Im v[0] never reach u.  Carried by the dc lane.
+        Cx<T> vN = ldcx(prm.v + ec * NH + H);
+        T fnN = ldcx(prm.fn + ec * NH + H).im;
+        float accN = prm.acc[ec * NH + H];
+        const T kwN = prm.kwave[H];
+        // 2-tap action basis: f_n = w0 a[i0] + w1 a[i1]; the actions are gathered straight from global memory
+        T a_tap[P][2][2], w_tap[P][2][2];
+        if ((flags & F_ACTIONS) && !(flags & F_BASIS_DENSE)) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = 2 * (p * TS + tl) + h;
+                    const int i0 = prm.tap_idx[2 * n], i1 = prm.tap_idx[2 * n + 1];
+                    w_tap[p][h][0] = prm.tap_w[2 * n];
+                    w_tap[p][h][1] = prm.tap_w[2 * n + 1];
+                    a_tap[p][h][0] = prm.actions[ec * prm.M + i0];
+                    a_tap[p][h][1] = prm.actions[ec * prm.M + i1];
+                }
+        }
+        const T v0im = v[0].im;                 // meaningful on the dc lane only
+
         // ---- per-register constants -------------------------------------------------------
         const T dt = prm.dt;
-        const T nu = prm.nu[ec];
         const T invN = T(1) / T(N);
-        int kk[P];
-        T kw[P], cv[P], cfo[P], cF[P];
+        T cv[P], cfo[P], cF[P];
         // v' = [(1-C) v - dt/2 (3 Fn - Fn_old) + dt F] / (1+C),  C = nu k^2 dt / 2  (Burger.py:486-488)
         //    = cv v + cfo (Fn_old - 3 Fn) + cF (dt F)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            kk[p] = f.k(p);
-            kw[p] = prm.kwave[kk[p]];
             const T C = T(0.5) * (kw[p] * kw[p]) * nu * dt;
             const T r = T(1) / (T(1) + C);
             cv[p] = (T(1) - C) * r;
             cfo[p] = T(0.5) * dt * r;
             cF[p] = q1 ? r : dt * r;
         }
-        const T kwN = prm.kwave[H];
         const T CN = T(0.5) * (kwN * kwN) * nu * dt;
         const T rN = T(1) / (T(1) + CN);
         const T cvN = (T(1) - CN) * rN, cfoN = T(0.5) * dt * rN, cFN = q1 ? rN : dt * rN;
@@ -119,23 +156,6 @@ struct BurgersWarp {
         const T scale_nl = T(0.5) * invN * invN;        // u is kept as U = N u in registers
         f.scaled_twiddles(scale_nl, ws_nl);
         f.scaled_twiddles(T(1), ws1);
-
-        // ---- load state ---------------------------------------------------------------------
-        const bool was_live = has && prm.status[ec] == 0;
-        bool live = was_live;
-        int iout = prm.iout[ec];
-        T tnow = prm.tnow[ec];
-        Cx<T> v[P], fn[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            v[p] = ldcx(prm.v + ec * NH + kk[p]);
-            fn[p] = ldcx(prm.fn + ec * NH + kk[p]);
-        }
-        // Nyquist mode: complex in the reference when the IC came from a truncated DNS spectrum
-        // (quirk Q5); its imaginary part and Im v[0] never reach u.  Carried by the dc lane.
-        Cx<T> vN = ldcx(prm.v + ec * NH + H);
-        T fnN = ldcx(prm.fn + ec * NH + H).im;
-        const T v0im = v[0].im;                 // meaningful on the dc lane only
 
         // ---- U = N * Re ifft(v) ---------------------------------------------------------------
         Cx<T> U[P], Uprev[P];
@@ -156,26 +176,28 @@ struct BurgersWarp {
 #pragma unroll
         for (int p = 0; p < P; ++p) { fa[p] = cx<T>(0, 0); Fa[p] = cx<T>(0, 0); }
         if (flags & F_ACTIONS) {
-            for (int i = tl; i < prm.M; i += TS) scratch[i] = prm.actions[ec * prm.M + i];
-            __syncwarp(f.c.tmask);
+            if (flags & F_BASIS_DENSE) {
+                for (int i = tl; i < prm.M; i += TS) scratch[i] = prm.actions[ec * prm.M + i];
+                __syncwarp(f.c.tmask);
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                T val[2];
+                for (int p = 0; p < P; ++p) {
+                    T val[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = 2 * (p * TS + tl) + h;
-                    T acc = T(0);
-                    if (flags & F_BASIS_DENSE) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = 2 * (p * TS + tl) + h;
+                        T acc = T(0);
                         for (int i = 0; i < prm.M; ++i) acc = fma(scratch[i], prm.basis[(size_t)i * N + n], acc);
-                    } else {
-                        acc = prm.tap_w[2 * n] * scratch[prm.tap_idx[2 * n]] +
-                              prm.tap_w[2 * n + 1] * scratch[prm.tap_idx[2 * n + 1]];
+                        val[h] = acc;
                     }
-                    val[h] = acc;
+                    fa[p] = cx<T>(val[0], val[1]);
                 }
-                fa[p] = cx<T>(val[0], val[1]);
+                __syncwarp(f.c.tmask);
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+                    fa[p] = cx<T>(w_tap[p][0][0] * a_tap[p][0][0] + w_tap[p][0][1] * a_tap[p][0][1],
+                                  w_tap[p][1][0] * a_tap[p][1][0] + w_tap[p][1][1] * a_tap[p][1][1]);
             }
-            __syncwarp(f.c.tmask);
             if (flags & F_DFORCE) {           // spectrum of a direct forcing is constant over the sub-steps
                 Cx<T> z[P];
 #pragma unroll
@@ -201,10 +223,6 @@ struct BurgersWarp {
         }
 
         // ---- reward bookkeeping ----------------------------------------------------------------
-        float acc32[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) acc32[p] = prm.acc[ec * NH + kk[p]];
-        float accN = prm.acc[ec * NH + H];
         const float dxf = (float)prm.dx, dtf = (float)dt;
         Cx<T> mse[P];
 #pragma unroll
@@ -216,6 +234,15 @@ struct BurgersWarp {
 
         // =============================== sub-steps ==============================================
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
+        T ek_ref[P];                       // reference spectrum row of the step this call ends at
+        const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
+        if (spec_reward) {
+            const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
+            const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
+#pragma unroll
+            for (int p = 0; p < P; ++p) ek_ref[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+        }
+        const T kprev_old = spec_reward ? prm.kprev[ec] : T(0);
         const bool hist = !LEAN && prm.hist_rows > 0;
         const bool do_mse = !LEAN && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
         const bool multi_col = !LEAN && prm.stepper > 1;
@@ -507,23 +534,19 @@ struct BurgersWarp {
             __syncwarp(f.c.tmask);
         }
 
-        if (prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0) {
+        if (spec_reward) {
             // burger_environment.py:172-176 on the running float32 sums
             const int A = prm.A;
-            const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
-            const int64_t row = iout < prm.ek_rows ? iout : prm.ek_rows - 1;
             T part = T(0);
 #pragma unroll
             for (int p = 0; p < P; ++p)
                 if (kk[p] >= 1) {
-                    const T ed = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
                     const T es = (T)((double)acc32[p] / (double)(iout + 1));
-                    const T q = fabs(ed - es) / ed;
+                    const T q = fabs(ek_ref[p] - es) / ek_ref[p];
                     part += q * q;
                 }
             part = team_sum(f, part) / T(H - 1);
-            const T prev = prm.kprev[ec];
-            const T r = live ? prev - part : -inf;
+            const T r = live ? kprev_old - part : -inf;
             if (has) {
                 for (int a = tl; a < A; a += TS) prm.reward_out[e * A + a] = r;
                 if (f.dc && live) prm.kprev[e] = part;
