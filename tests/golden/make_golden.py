@@ -374,6 +374,47 @@ def gen_fd():
     save("fd.npz", **bundle)
 
 
+# --------------------------------------------------------------------------- KS environment
+def gen_ks_env():
+    """The reference ks_environment.setup_dns_default + environment with a fake Korali sample
+    (DNS N = 256 instead of the script default to keep the fixture small)."""
+    import ks_environment as KE
+    bundle = {}
+    UNSEEDED[0] = 777
+    NDNS, dt, g, epl = 256, 0.25, 32, 50          # nIntermediate = int(500/0.25/50) = 40
+    captured = {}
+    orig_ic = RK.KS.IC
+
+    def spy_ic(self, u0=None, v0=None, case='noise', seed=42):
+        r = orig_ic(self, u0=u0, v0=v0, case=case, seed=seed)
+        if u0 is None and v0 is None and 'transient_u0' not in captured:
+            captured['transient_u0'] = self.u0.copy()
+        return r
+
+    RK.KS.IC = spy_ic
+    KE.KS = RK.KS
+    dns = KE.setup_dns_default(NDNS, dt, 1.0, 42)
+    RK.KS.IC = orig_ic
+    for tag, dforce in (("direct", True), ("eddy", False)):
+        rng = np.random.default_rng(21)
+        acts = rng.normal(0.0, 0.05 if dforce else 0.01, (epl, 16))
+        s = FakeSample([a.tolist() for a in acts])
+        KE.environment(s, NDNS, g, 16, dt, 1.0, epl, dforce, 42, dns)
+        assert s["Termination"] == "Terminal"
+        p = f"{tag}/"
+        bundle[p + "actions"] = acts
+        bundle[p + "state0"] = s.state0
+        bundle[p + "states"] = np.array(s.states + [np.array(s["State"], dtype=float)])
+        bundle[p + "rewards"] = np.array(s.rewards + [np.array(s["Reward"], dtype=float)])
+    bundle["transient_u0"] = captured['transient_u0']
+    bundle["dns_u0"] = np.array(dns.u0)
+    bundle["dns_vv0"] = dns.vv[0].copy()
+    bundle["dns_Ek_ktt"] = dns.Ek_ktt[:, :g // 2].copy()
+    bundle["dns_uu_last"] = np.array(dns.uu[-1])
+    bundle["cfg"] = np.array([NDNS, dt, g, epl, 16])
+    save("ks_env.npz", **bundle)
+
+
 if __name__ == "__main__":
     np.seterr(over="raise", invalid="raise")
     gen_burger_steps()
@@ -382,3 +423,4 @@ if __name__ == "__main__":
     gen_burger_dns()
     gen_ks()
     gen_fd()
+    gen_ks_env()

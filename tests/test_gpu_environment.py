@@ -95,3 +95,42 @@ def test_batched_episode_equals_single_sample_episodes(golden):
             assert np.array_equal(states[i], st[i][e].cpu().numpy()), (e, i)
         for i in range(epl):
             assert float(rewards[i]) == float(rws[i][e, 0]), (e, i)
+
+
+@pytest.mark.parametrize("tag,dforce", [("direct", True), ("eddy", False)])
+def test_ks_environment_function_matches_reference_episode(golden, tag, dforce):
+    """marlpde_b200.ks_environment.environment against the reference's ks_environment.environment
+    (fake Korali sample, recorded DNS spectrum; the DNS itself is chaotic and not comparable run to run)."""
+    import types
+    import marlpde_b200.ks_environment as ke
+    g = golden("ks_env.npz")
+    NDNS, dt, gsz, epl, M = g["cfg"]
+    NDNS, gsz, epl, M = int(NDNS), int(gsz), int(epl), int(M)
+    dns = types.SimpleNamespace(N=NDNS, vv=g["dns_vv0"][None], Ek_ktt=g["dns_Ek_ktt"])
+    acts = g[tag + "/actions"]
+    s = FakeSample([a.tolist() for a in acts])
+    ke.environment(s, NDNS, gsz, M, dt, 1.0, epl, dforce, 42, dns)
+    assert s["Termination"] == "Terminal"
+    states = np.array(s.states + [np.array(s["State"], dtype=float)])
+    rewards = np.array(s.rewards + [np.array(s["Reward"], dtype=float)])
+    dx = 22 / gsz
+    noise = 16 * np.finfo(np.float32).eps * 4.0 / dx ** 2         # float32 field, second difference (quirk Q7)
+    assert np.max(np.abs(s.state0 - g[tag + "/state0"])) <= noise
+    # 40 chaotic ETDRK4 steps per action amplify round-off: compare the early episode tightly, all of it loosely
+    assert np.max(np.abs(states[:5] - g[tag + "/states"][:5])) <= 50 * noise
+    np.testing.assert_allclose(rewards[:5], g[tag + "/rewards"][:5], rtol=1e-3, atol=1e-7)
+    if dforce:     # (the float32-row forcing of dforce=False seeds 1e-7 differences that the chaotic dynamics amplify)
+        assert np.corrcoef(rewards, g[tag + "/rewards"])[0, 1] > 0.99
+    else:
+        np.testing.assert_allclose(rewards[:10], g[tag + "/rewards"][:10], rtol=5e-2, atol=1e-6)
+
+
+def test_ks_dns_setup_runs_and_has_the_reference_spectrum(golden):
+    """setup_dns_default (transient + restart + main run) from the recorded noise IC: the trajectory is chaotic,
+    but the time-averaged spectrum of the attractor matches the reference DNS."""
+    import marlpde_b200.ks_environment as ke
+    g = golden("ks_env.npz")
+    dns = ke.setup_dns_default(256, 0.25, 1.0, 42, u0=g["transient_u0"])
+    assert dns.ioutnum == 2000 and int(dns.status) == 0
+    ek = dns.Ek_ktt.cpu().numpy()[-1, 1:9]
+    np.testing.assert_allclose(ek, g["dns_Ek_ktt"][-1, 1:9], rtol=0.35)
