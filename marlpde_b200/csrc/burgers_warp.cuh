@@ -471,7 +471,8 @@ struct BurgersWarp {
                 stcx(prm.v + e * NH + kk[p], v[p]);
                 stcx(prm.fn + e * NH + kk[p], fn[p]);
                 prm.acc[e * NH + kk[p]] = acc32[p];
-                stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
+                if (prm.version == 1)      // u before the last sub-step: only state version 1 (dudt) reads it
+                    stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
             }
             if (f.dc) {
                 stcx(prm.v + e * NH + H, vN);
@@ -483,7 +484,35 @@ struct BurgersWarp {
         }
 
         const T inf = T(1) / T(0);
-        if (prm.state_out) {
+        if (prm.state_out && prm.A == 1 && prm.version <= 2) {
+            // getState, single agent, versions 0/1/2 (Burger.py:617-622): rows are per-point fields, so the
+            // lane's two adjacent points go out as one 16-byte store each -- no shared-memory gather
+            const int ver = prm.version;
+            T left[P], right[P];
+            halo(f, U, left, right);
+            const T sd2 = inv_dx2 * invN, sdt = invN / dt;
+            if (has) {
+                Cx<T>* row0 = reinterpret_cast<Cx<T>*>(prm.state_out + e * (ver == 0 ? N : 2 * N));
+                Cx<T>* row1 = row0 + H;
+                const Cx<T> ii = cx<T>(inf, inf);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const int j = p * TS + tl;
+                    const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
+                    const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2, (U[p].re - T(2) * U[p].im + right[p]) * sd2);
+                    if (ver == 0) {
+                        stcx(row0 + j, live ? d2 : ii);
+                    } else if (ver == 1) {
+                        const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
+                        stcx(row0 + j, live ? dudt : ii);
+                        stcx(row1 + j, live ? d2 : ii);
+                    } else {
+                        stcx(row0 + j, live ? u : ii);
+                        stcx(row1 + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
+                    }
+                }
+            }
+        } else if (prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store
             const int ver = prm.version, A = prm.A;
