@@ -162,6 +162,26 @@ int mpde_set(mpde_env* env, int32_t field, const void* src_dev, void* stream);
 /* introspection for the bench: kernels launched so far by this handle */
 int64_t mpde_launch_count(const mpde_env* env);
 
+/* ---- peer-memory gather of per-environment summaries (multi-GPU, one process per GPU, one node) ------------
+ * The reference is serial; this is the learner-side exchange of a sharded batch.  Buffers are
+ * cudaMalloc'ed by the library, shared with the other ranks of the node through CUDA IPC handles, and written
+ * with plain stores over NVLink by mpde_peer_put (no NCCL call, no host round trip per step).
+ *   alloc/free   : device buffer that can be exported
+ *   export/open  : 64-byte IPC handle of a buffer / map a peer's buffer into this process
+ *   put          : copy `nbytes` from `src` into EVERY rank's gather buffer at `dst_offset_bytes`, then publish
+ *                  `step` in slot `my_rank` of every rank's flag array (int64 [nranks])
+ *   wait         : make `stream` wait until all slots of this rank's flag array are >= step; bounded by
+ *                  `max_spins` polls per source -- a missing peer sets *err_dev = 1 + rank instead of hanging */
+int mpde_peer_alloc(size_t bytes, void** out);
+int mpde_peer_free(void* p);
+int mpde_peer_export(void* dev_ptr, void* handle64);
+int mpde_peer_open(const void* handle64, void** out);
+int mpde_peer_close(void* p);
+int mpde_peer_put(const void* src, size_t nbytes, void* const* dst_ptrs, size_t dst_offset_bytes, void* const* flag_ptrs,
+                  int32_t my_rank, int32_t nranks, int64_t step, void* counter_dev, void* stream);
+int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err_dev, int64_t max_spins, void* stream);
+const char* mpde_peer_last_error(void);
+
 const char* mpde_last_error(void);
 int mpde_abi_version(void);
 

@@ -54,6 +54,14 @@ SIGNATURES = {
     "mpde_get": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mpde_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mpde_launch_count": (_i64, [_vp]),
+    "mpde_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "mpde_peer_free": (C.c_int, [_vp]),
+    "mpde_peer_export": (C.c_int, [_vp, _vp]),
+    "mpde_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mpde_peer_close": (C.c_int, [_vp]),
+    "mpde_peer_put": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), C.c_size_t, C.POINTER(_vp), _i32, _i32, _i64, _vp, _vp]),
+    "mpde_peer_wait": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp]),
+    "mpde_peer_last_error": (C.c_char_p, []),
     "mpde_last_error": (C.c_char_p, []),
     "mpde_abi_version": (C.c_int, []),
 }

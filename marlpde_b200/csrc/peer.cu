@@ -1,0 +1,124 @@
+// Peer-memory gather of per-environment summaries over NVLink (no NCCL call, no host round trip):
+// every rank's step kernel writes state + reward into a flat local slab; peer_put_kernel stores that
+// slab into the gather buffer of EVERY rank (plain 16-byte stores to peer-mapped pointers travel over
+// NVLink / NVSwitch) and then publishes a per-source step counter; peer_wait_kernel makes the consumer
+// stream wait until all sources have published the current step.  Buffers come from cudaMalloc and are
+// shared between the one-process-per-GPU ranks of a node through CUDA IPC handles.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../include/marlpde_b200.h"
+
+namespace {
+thread_local std::string g_perr;
+int pfail(const std::string& m) { g_perr = m; return -1; }
+#define PCU(call)                                                                      \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) return pfail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+constexpr int MAX_RANKS = 16;
+struct PeerTable {
+    void* dst[MAX_RANKS];          // gather buffer of rank p (peer-mapped)
+    long long* flags[MAX_RANKS];   // flag array [nranks] of rank p (peer-mapped)
+};
+
+__global__ void peer_put_kernel(const int4* __restrict__ src, size_t n16, PeerTable tab, size_t dst_off16, int my_rank,
+                                int nranks, long long step, unsigned int* counter) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const int4 v = src[i];
+        for (int p = 0; p < nranks; ++p) reinterpret_cast<int4*>(tab.dst[p])[dst_off16 + i] = v;
+    }
+    __threadfence_system();                       // this block's stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        if (ticket == gridDim.x - 1) {            // ... and the last block to finish publishes the step
+            *counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < nranks; ++p) *reinterpret_cast<volatile long long*>(tab.flags[p] + my_rank) = step;
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void peer_wait_kernel(const long long* flags, int nranks, long long step, int* err, long long max_spins) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const volatile long long* f = flags + r;
+        long long spins = 0;
+        while (*f < step) {
+            if (++spins > max_spins) {            // bounded: a missing peer becomes an error flag, never a hang
+                atomicExch(err, 1 + r);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+}  // namespace
+
+extern "C" {
+
+const char* mpde_peer_last_error(void) { return g_perr.c_str(); }
+
+int mpde_peer_alloc(size_t bytes, void** out) {
+    if (!out) return pfail("null argument");
+    PCU(cudaMalloc(out, bytes));
+    PCU(cudaMemset(*out, 0, bytes));
+    return 0;
+}
+int mpde_peer_free(void* p) {
+    PCU(cudaFree(p));
+    return 0;
+}
+int mpde_peer_export(void* dev_ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    PCU(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), dev_ptr));
+    return 0;
+}
+int mpde_peer_open(const void* handle64, void** out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    PCU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int mpde_peer_close(void* p) {
+    PCU(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+
+int mpde_peer_put(const void* src, size_t nbytes, void* const* dst_ptrs, size_t dst_offset_bytes, void* const* flag_ptrs,
+                  int32_t my_rank, int32_t nranks, int64_t step, void* counter_dev, void* stream) {
+    if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_put: 1..16 ranks");
+    if ((nbytes & 15) || (dst_offset_bytes & 15)) return pfail("peer_put: sizes/offsets must be multiples of 16 bytes");
+    PeerTable tab;
+    for (int p = 0; p < nranks; ++p) {
+        tab.dst[p] = dst_ptrs[p];
+        tab.flags[p] = static_cast<long long*>(flag_ptrs[p]);
+    }
+    const size_t n16 = nbytes / 16;
+    int grid = (int)((n16 + 255) / 256);
+    if (grid > 64) grid = 64;
+    if (grid < 1) grid = 1;
+    peer_put_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const int4*>(src), n16, tab, dst_offset_bytes / 16,
+                                                                         my_rank, nranks, (long long)step,
+                                                                         static_cast<unsigned int*>(counter_dev));
+    PCU(cudaGetLastError());
+    return 0;
+}
+
+int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err_dev, int64_t max_spins, void* stream) {
+    if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait: 1..16 ranks");
+    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks, (long long)step,
+                                                                      static_cast<int*>(err_dev), (long long)max_spins);
+    PCU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -56,6 +56,97 @@ def gather_envs(local, out=None):
     return out
 
 
+class _RawDeviceMemory:
+    """Expose a raw device pointer to torch through the CUDA array interface (no copy, no ownership)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """All-gather of one fixed-size slab per rank through peer-mapped memory (NVLink stores issued by a small
+    CUDA kernel, no NCCL call per step).  See include/marlpde_b200.h, "peer-memory gather".
+
+    put(src)  : enqueue the copy of this rank's slab into every rank's ``gathered[rank]`` + publish the step
+    wait()    : make the current stream wait until every rank's slab of the current step has landed here
+    gathered  : [world_size, chunk_elems] tensor living in this rank's exported buffer
+    """
+
+    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24):
+        import ctypes as C
+        from . import _lib as LB
+        self._C, self._lib = C, LB.lib()
+        self.rank, self.ws = world()
+        self.device = torch.device(device)
+        item = torch.empty((), dtype=dtype).element_size()
+        self.chunk_bytes = (chunk_elems * item + 15) // 16 * 16
+        self.chunk_elems, self.dtype, self.max_spins = chunk_elems, dtype, int(max_spins)
+        gbytes = self.ws * self.chunk_bytes
+        total = gbytes + 16 * ((self.ws * 8 + 15) // 16)
+        base = C.c_void_p()
+        self._check(self._lib.mpde_peer_alloc(total, C.byref(base)))
+        self._base = base.value
+        handle = (C.c_ubyte * 64)()
+        self._check(self._lib.mpde_peer_export(self._base, handle))
+        handles = [None] * self.ws
+        if self.ws > 1:
+            dist.all_gather_object(handles, bytes(handle))
+        self._peer_bases, self._opened = [], []
+        for r in range(self.ws):
+            if r == self.rank:
+                self._peer_bases.append(self._base)
+            else:
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                self._check(self._lib.mpde_peer_open(buf, C.byref(p)))
+                self._peer_bases.append(p.value)
+                self._opened.append(p.value)
+        arr = C.c_void_p * self.ws
+        self._dst = arr(*[b for b in self._peer_bases])
+        self._flags = arr(*[b + gbytes for b in self._peer_bases])
+        self._my_flags = self._base + gbytes
+        raw = torch.as_tensor(_RawDeviceMemory(self._base, gbytes), device=self.device)
+        self.gathered = raw.view(self.ws, self.chunk_bytes).view(dtype)[:, :chunk_elems]
+        self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._err = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.step = 0
+        if self.ws > 1:
+            dist.barrier()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("marlpde_b200 peer: " + self._lib.mpde_peer_last_error().decode())
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def put(self, src):
+        assert src.is_cuda and src.is_contiguous() and src.numel() * src.element_size() <= self.chunk_bytes
+        self.step += 1
+        nbytes = (src.numel() * src.element_size() + 15) // 16 * 16
+        self._check(self._lib.mpde_peer_put(src.data_ptr(), nbytes, self._dst, self.rank * self.chunk_bytes, self._flags,
+                                            self.rank, self.ws, self.step, self._counter.data_ptr(), self._stream()))
+
+    def wait(self):
+        self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err.data_ptr(), self.max_spins,
+                                             self._stream()))
+
+    def check(self):
+        e = int(self._err[0])
+        if e:
+            raise RuntimeError(f"peer gather timed out waiting for rank {e - 1}")
+
+    def close(self):
+        if getattr(self, "_base", None):
+            torch.cuda.synchronize(self.device)
+            if self.ws > 1:
+                dist.barrier()
+            for p in self._opened:
+                self._lib.mpde_peer_close(p)
+            self._lib.mpde_peer_free(self._base)
+            self._base = None
+
+
 class ShardedBatch:
     """A batch of ``n_global`` environments split over the ranks of the current process group.
 
@@ -65,8 +156,9 @@ class ShardedBatch:
     single all-gather delivers to every rank (the learner reads ``states`` / ``rewards`` views).
     """
 
-    def __init__(self, n_global, factory):
+    def __init__(self, n_global, factory, transport="nccl"):
         self.rank, self.world_size = world()
+        self.transport = transport
         self.n_global = int(n_global)
         self.lo, self.hi = shard_range(self.n_global, self.rank, self.world_size)
         self.ids = np.arange(self.lo, self.hi)
@@ -79,7 +171,12 @@ class ShardedBatch:
             buf = self.env._state_buf
             self._flat = torch.zeros(nl * (S + A), dtype=buf.dtype, device=buf.device)
             self.env.bind_output(self._flat[:nl * S].view(nl, S), self._flat[nl * S:].view(nl, A))
-            self._gflat = torch.zeros((self.world_size, nl * (S + A)), dtype=buf.dtype, device=buf.device)
+            if transport == "p2p":
+                self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device)
+                self._gflat = self._peer.gathered
+            else:
+                self._peer = None
+                self._gflat = torch.zeros((self.world_size, nl * (S + A)), dtype=buf.dtype, device=buf.device)
         self._g_state = self._g_reward = None
         self._work = None
 
@@ -88,7 +185,10 @@ class ShardedBatch:
 
     def wait(self):
         """Block the current stream until the last asynchronous gather has landed."""
-        if self._work is not None:
+        if self._work == "p2p":
+            self._peer.wait()
+            self._work = None
+        elif self._work is not None:
             self._work.wait()
             self._work = None
 
@@ -105,7 +205,12 @@ class ShardedBatch:
         self.wait()                                   # the send buffer is about to be overwritten
         st, rw = self.env.step_n(a, n, **kw)
         if self._flat is not None and st is not None and rw is not None:
-            if self.world_size == 1:
+            if self._peer is not None:
+                self._peer.put(self._flat)
+                self._work = "p2p"
+                if not async_gather:
+                    self.wait()
+            elif self.world_size == 1:
                 self._gflat[0].copy_(self._flat)
             else:
                 self._work = dist.all_gather_into_tensor(self._gflat.view(-1), self._flat, async_op=True)

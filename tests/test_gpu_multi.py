@@ -25,30 +25,35 @@ def _acts():
     return torch.as_tensor(np.random.default_rng(1).uniform(0.0, 0.05, (B, M)))
 
 
-def _worker(rank, ws, port, q):
+def _worker(rank, ws, port, q, transport="nccl"):
     import torch.distributed as dist
     from marlpde_b200 import dist as mdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
     try:
-        sb = mdist.ShardedBatch(B, _factory)
+        sb = mdist.ShardedBatch(B, _factory, transport=transport)
         a = _acts().cuda()
         for _ in range(3):
             gs, gr = sb.step_n(a, 10)
         torch.cuda.synchronize()
+        if transport == "p2p":
+            sb._peer.check()
         q.put((rank, gs.cpu().numpy(), gr.cpu().numpy()))
+        if transport == "p2p":
+            sb._peer.close()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_shards_equal_one_gpu_bitwise():
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     import torch.multiprocessing as mp
-    ws, port = 2, 29500 + os.getpid() % 400
+    ws, port = 2, 29500 + os.getpid() % 400 + (50 if transport == "p2p" else 0)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, q, transport)) for r in range(ws)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=300) for _ in range(ws)], key=lambda t: t[0])
@@ -62,3 +67,17 @@ def test_two_gpu_shards_equal_one_gpu_bitwise():
     for o in outs:
         assert np.array_equal(o[1], st.cpu().numpy())
         assert np.array_equal(o[2], rw.cpu().numpy())
+
+
+def test_peer_gather_single_rank_roundtrip():
+    """PeerGather degenerates to a local copy + flag handshake on one GPU (runs in the 1-GPU suite)."""
+    from marlpde_b200.dist import PeerGather
+    pg = PeerGather(1000, torch.float64, "cuda:0")
+    x = torch.arange(1000, dtype=torch.float64, device="cuda:0")
+    for k in range(3):
+        pg.put(x + k)
+        pg.wait()
+        torch.cuda.synchronize()
+        pg.check()
+        assert torch.equal(pg.gathered[0], x + k)
+    pg.close()
