@@ -5,34 +5,52 @@
 
 namespace mpde {
 
-// register budget: one wave of warps must fit for the small-batch (latency) regime
+// Register budget.  CTAs are 64 threads (2 warps).  The hot case -- fp64, N = 32, 16 lanes per environment,
+// B = 4096 -> 2048 warps = 13.8 per SM -- must be resident in ONE wave: 7 CTAs per SM = 144 registers per thread
+// (at 128 ptxas shuffles 64-bit values through XOR swaps and moves: +50 instructions per sub-step).
 template <typename T, int N, int TS>
 constexpr int min_blocks() {
     constexpr int P = N / 2 / TS;
-    return (sizeof(T) == 8 ? (P <= 1 ? 8 : (P <= 2 ? 6 : 4)) : (P <= 2 ? 8 : 4));
+    if (sizeof(T) == 8 && N == 32 && P == 1) return 7;
+    return 4 * (sizeof(T) == 8 ? (P <= 1 ? 2 : 1) : (P <= 2 ? 2 : 1));
 }
+#if defined(MPDE_LB_T) && defined(MPDE_LB_B)      // tuning override: -DMPDE_LB_T=64 -DMPDE_LB_B=7
+#define MPDE_LB MPDE_LB_T, MPDE_LB_B
+#else
+#define MPDE_LB 64, min_blocks<T, N, TS>()
+#endif
+constexpr int WARPS_PER_CTA = 2;
 
-// 256 threads x (min_blocks / 4) CTAs give the same register budget as 64 x min_blocks
 template <typename T, int N, int TS, int SF, bool LEAN>
-__global__ void __launch_bounds__(256, (min_blocks<T, N, TS>() / 4 > 0 ? min_blocks<T, N, TS>() / 4 : 1)) burgers_warp_kernel(const SpectralParams<T> prm) {
+__global__ void __launch_bounds__(MPDE_LB) burgers_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BurgersWarp<T, N, TS, SF, LEAN>::run(prm, reinterpret_cast<T*>(smem_raw));
+    BurgersWarp<T, N, TS, SF, LEAN>::publish(prm);
 }
 
 template <typename T, int N, int TS, int SF, bool LEAN = false>
 int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
     constexpr int TPW = 32 / TS;
     const int64_t warps = (p.B + TPW - 1) / TPW;
-    int wpc = 2;                                   // warps per CTA (MPDE_WPC = 1, 2, 4, 8 overrides: tuning)
-    if (const char* s = std::getenv("MPDE_WPC")) {
-        const int v = std::atoi(s);
-        if (v == 1 || v == 2 || v == 4 || v == 8) wpc = v;
-    }
+    constexpr int wpc = WARPS_PER_CTA;
     const int block = 32 * wpc;
     const int grid = (int)((warps + wpc - 1) / wpc);
-    const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
+    const int scr = (p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2) + BurgersWarp<T, N, TS, SF, LEAN>::STASH;
     const size_t smem = (size_t)wpc * TPW * scr * sizeof(T);
-    burgers_warp_kernel<T, N, TS, SF, LEAN><<<grid, block, smem, st>>>(p);
+    // programmatic dependent launch: this kernel may become resident (and read its constant tables) while the
+    // previous kernel of the stream drains; it reads mutable state only after pdl_wait().  MPDE_PDL=0 disables.
+    static const bool pdl = [] { const char* s = std::getenv("MPDE_PDL"); return !(s && s[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, burgers_warp_kernel<T, N, TS, SF, LEAN>, p);
     return 1;
 }
 
@@ -40,7 +58,7 @@ int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
 // history / MSE / multi-column-forcing branches when the call does not need them
 template <typename T, int N, int TS, int SF>
 int launch_warp_lean(const SpectralParams<T>& p, cudaStream_t st) {
-    const bool lean = p.hist_rows == 0 && !(p.reward_mode == REWARD_MSE && p.truth) && p.stepper == 1;
+    const bool lean = p.hist_rows == 0 && !(p.reward_mode == REWARD_MSE && p.truth) && p.stepper == 1 && p.version != 1;
     return lean ? launch_warp<T, N, TS, SF, true>(p, st) : launch_warp<T, N, TS, SF, false>(p, st);
 }
 template <typename T, int N, int TS>

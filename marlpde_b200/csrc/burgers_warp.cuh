@@ -30,11 +30,14 @@ __device__ __forceinline__ float ek_row_f32(float re, float im, int N, float dxf
 }
 
 // LEAN: compile-time promise of the common training configuration -- no history buffers, no MSE
-// truth table, forcing column period 1 -- which removes those branches from the sub-step loop.
+// truth table, forcing column period 1, state version != 1 (no dudt, so u_prev is not tracked) --
+// which removes those branches and registers from the sub-step loop.
 template <typename T, int N, int TS_, int SF, bool LEAN = false>
 struct BurgersWarp {
     using R = RealFFT<T, N, TS_>;
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
+    // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row
+    static constexpr int STASH = 6 + H;
 
     // all cross-lane traffic is scoped to the team (f.c.tmask): teams share a warp but never
     // each other's control flow or data
@@ -80,7 +83,7 @@ struct BurgersWarp {
         const int warp = threadIdx.x >> 5;
         const int wpc = blockDim.x >> 5;
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
-        if (first >= prm.B) return;                                  // whole warp idle
+        if (first >= prm.B) return;                                  // whole warp idle (publish() still runs in the kernel)
         R f;
         f.init(prm.tw);
         const int tl = f.c.tl;
@@ -90,26 +93,45 @@ struct BurgersWarp {
         const int64_t ec = has ? e : 0;
         const int flags = SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF);
         const bool q1 = !(flags & F_FORCING);
-        const int scr = max(prm.M, 2 * N + N / 2);
+        const int scr = max(prm.M, 2 * N + N / 2) + STASH;
         T* scratch = smem + (size_t)(warp * TPW + team) * scr;
+        T* stash = scratch + (scr - STASH);      // per-team constants parked in shared memory (register relief)
 
-        // ---- issue every global load of the prologue up front (one memory round trip) ---------------
+        // ---- constant tables first: they may be read while the previous kernel of the stream still runs ----
         int kk[P];
+        T kw[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) kk[p] = f.k(p);
+        for (int p = 0; p < P; ++p) { kk[p] = f.k(p); kw[p] = prm.kwave[kk[p]]; }
+        const T kwN = prm.kwave[H];
+        const bool sparse_actions = (flags & F_ACTIONS) && !(flags & F_BASIS_DENSE);
+        int i_tap[P][2][2];
+        T w_tap[P][2][2];
+        if (sparse_actions) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = 2 * (p * TS + tl) + h;
+                    i_tap[p][h][0] = prm.tap_idx[2 * n];
+                    i_tap[p][h][1] = prm.tap_idx[2 * n + 1];
+                    w_tap[p][h][0] = prm.tap_w[2 * n];
+                    w_tap[p][h][1] = prm.tap_w[2 * n + 1];
+                }
+        }
+        pdl_wait();
+        pdl_launch_dependents();
+        // ---- issue every global load of the mutable state up front (one memory round trip) -----------
         const bool was_live = has && prm.status[ec] == 0;
         bool live = was_live;
         int iout = prm.iout[ec];
         T tnow = prm.tnow[ec];
         const T nu = prm.nu[ec];
         Cx<T> v[P], fn[P];
-        T kw[P];
         float acc32[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             v[p] = ldcx(prm.v + ec * NH + kk[p]);
             fn[p] = ldcx(prm.fn + ec * NH + kk[p]);
-            kw[p] = prm.kwave[kk[p]];
             acc32[p] = prm.acc[ec * NH + kk[p]];
         }
         // Nyquist mode: complex in the reference when the IC came from a truncated DNS spectrum
@@ -117,20 +139,15 @@ struct BurgersWarp {
         Cx<T> vN = ldcx(prm.v + ec * NH + H);
         T fnN = ldcx(prm.fn + ec * NH + H).im;
         float accN = prm.acc[ec * NH + H];
-        const T kwN = prm.kwave[H];
         // 2-tap action basis: f_n = w0 a[i0] + w1 a[i1]; the actions are gathered straight from global memory
-        T a_tap[P][2][2], w_tap[P][2][2];
-        if ((flags & F_ACTIONS) && !(flags & F_BASIS_DENSE)) {
+        T a_tap[P][2][2];
+        if (sparse_actions) {
 #pragma unroll
             for (int p = 0; p < P; ++p)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int n = 2 * (p * TS + tl) + h;
-                    const int i0 = prm.tap_idx[2 * n], i1 = prm.tap_idx[2 * n + 1];
-                    w_tap[p][h][0] = prm.tap_w[2 * n];
-                    w_tap[p][h][1] = prm.tap_w[2 * n + 1];
-                    a_tap[p][h][0] = prm.actions[ec * prm.M + i0];
-                    a_tap[p][h][1] = prm.actions[ec * prm.M + i1];
+                    a_tap[p][h][0] = prm.actions[ec * prm.M + i_tap[p][h][0]];
+                    a_tap[p][h][1] = prm.actions[ec * prm.M + i_tap[p][h][1]];
                 }
         }
         const T v0im = v[0].im;                 // meaningful on the dc lane only
@@ -149,12 +166,23 @@ struct BurgersWarp {
             cfo[p] = T(0.5) * dt * r;
             cF[p] = q1 ? r : dt * r;
         }
-        const T CN = T(0.5) * (kwN * kwN) * nu * dt;
-        const T rN = T(1) / (T(1) + CN);
-        const T cvN = (T(1) - CN) * rN, cfoN = T(0.5) * dt * rN, cFN = q1 ? rN : dt * rN;
-        Cx<T> ws_nl[P], ws1[P];
-        const T scale_nl = T(0.5) * invN * invN;        // u is kept as U = N u in registers
-        f.scaled_twiddles(scale_nl, ws_nl);
+        // u is kept as U = N u in registers and the transforms are unscaled: the factor 1/(2 N^2) of
+        // fft(u^2 / 2) is folded into the wavenumber that multiplies it (Fn = i k X)
+        const T scale_nl = T(0.5) * invN * invN;
+        T kws[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) kws[p] = kw[p] * scale_nl;
+        {
+            const T CN = T(0.5) * (kwN * kwN) * nu * dt;
+            const T rN = T(1) / (T(1) + CN);
+            if (f.dc) {
+                stash[0] = (T(1) - CN) * rN;          // cvN
+                stash[1] = T(0.5) * dt * rN;          // cfoN
+                stash[2] = q1 ? rN : dt * rN;         // cFN
+                stash[3] = kwN * scale_nl;            // kwN (scaled)
+            }
+        }
+        Cx<T> ws1[P];
         f.scaled_twiddles(T(1), ws1);
 
         // ---- U = N * Re ifft(v) ---------------------------------------------------------------
@@ -162,7 +190,8 @@ struct BurgersWarp {
         f.inv(v, vN.re, U);
 #pragma unroll
         for (int p = 0; p < P; ++p) Uprev[p] = U[p];
-        if ((flags & F_NO_ADVANCE) && prm.version == 1 && iout > 0) {
+        const bool v1 = !LEAN && prm.version == 1;             // state version 1 needs u of the previous step (dudt)
+        if ((flags & F_NO_ADVANCE) && v1 && iout > 0) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const Cx<T> t = ldcx(reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N) + p * TS + tl);
@@ -234,15 +263,17 @@ struct BurgersWarp {
 
         // =============================== sub-steps ==============================================
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
-        T ek_ref[P];                       // reference spectrum row of the step this call ends at
+        // reference spectrum row of the step this call ends at + kPrevRelErr: fetched now (off the critical
+        // path of the epilogue), parked in shared memory until the reward is evaluated
         const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
         if (spec_reward) {
             const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
             const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
 #pragma unroll
-            for (int p = 0; p < P; ++p) ek_ref[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+            for (int p = 0; p < P; ++p) stash[5 + kk[p]] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+            if (f.dc) stash[4] = prm.kprev[ec];
         }
-        const T kprev_old = spec_reward ? prm.kprev[ec] : T(0);
+        __syncwarp(f.c.tmask);
         const bool hist = !LEAN && prm.hist_rows > 0;
         const bool do_mse = !LEAN && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
         const bool multi_col = !LEAN && prm.stepper > 1;
@@ -263,9 +294,9 @@ struct BurgersWarp {
                 for (int p = 0; p < P; ++p)
                     zf[p] = cx<T>(fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
                                   fa[p].im * (U[p].re - T(2) * U[p].im + right[p]));
-                f.fwd2(z, X, XN, scale_nl, ws_nl, zf, S, SN, T(1), ws1);
+                f.fwd2(z, X, XN, T(1), ws1, zf, S, SN, T(1), ws1);
             } else {
-                f.fwd(z, X, XN, scale_nl, ws_nl);
+                f.fwd(z, X, XN, T(1), ws1);
             }
 
             Cx<T> Fh[P];
@@ -300,8 +331,8 @@ struct BurgersWarp {
                     Cx<T> w[P], L1[P], uh[P];
 #pragma unroll
                     for (int p = 0; p < P; ++p)      // filtered fft(u^2) = 2 X
-                        w[p] = cut[p] ? cx<T>(0, 0) : cx<T>(T(2) * X[p].re, T(2) * X[p].im);
-                    f.inv(w, cutN ? T(0) : T(2) * XN, L1);
+                        w[p] = cut[p] ? cx<T>(0, 0) : cx<T>((T(2) * scale_nl) * X[p].re, (T(2) * scale_nl) * X[p].im);
+                    f.inv(w, cutN ? T(0) : (T(2) * scale_nl) * XN, L1);
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         L1[p] = cx<T>(L1[p].re * (T(0.5) * invN), L1[p].im * (T(0.5) * invN));
@@ -389,8 +420,8 @@ struct BurgersWarp {
             // (Burger.py:488) is a complex64 product: float32(dt) * float32(F), rounded to float32.
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                if (it == nsub - 1) Uprev[p] = U[p];       // u before the last sub-step (dudt of state v1)
-                const Cx<T> fnn = cx<T>(-kw[p] * X[p].im, kw[p] * X[p].re);                // i k X
+                if (!LEAN && it == nsub - 1) Uprev[p] = U[p];       // u before the last sub-step (dudt of state v1)
+                const Cx<T> fnn = cx<T>(-kws[p] * X[p].im, kws[p] * X[p].re);              // i k X
                 const Cx<T> F = q1 ? cx<T>((T)__fmul_rn(dtf, (float)Fh[p].re), (T)__fmul_rn(dtf, (float)Fh[p].im)) : Fh[p];
                 v[p] = cx<T>(fma(cF[p], F.re, fma(cfo[p], fma(T(-3), fnn.re, fn[p].re), cv[p] * v[p].re)),
                              fma(cF[p], F.im, fma(cfo[p], fma(T(-3), fnn.im, fn[p].im), cv[p] * v[p].im)));
@@ -398,7 +429,8 @@ struct BurgersWarp {
                 bad |= blown(v[p]);
             }
             {   // k = 0: Fn = 0, F real -> Im v[0] is a constant of the motion; Nyquist: F real, Fn imaginary
-                const T fnnN = kwN * XN;
+                const T cvN = stash[0], cfoN = stash[1], cFN = stash[2];
+                const T fnnN = stash[3] * XN;
                 const T FN = q1 ? (T)__fmul_rn(dtf, (float)FhN) : FhN;
                 vN = cx<T>(fma(cFN, FN, cvN * vN.re), fma(cfoN, fma(T(-3), fnnN, fnN), cvN * vN.im));
                 fnN = fnnN;
@@ -408,7 +440,6 @@ struct BurgersWarp {
                 }
             }
             iout += 1;
-            tnow += dt;
 
             // U = N Re ifft(v) (Burger.py:491)
             f.inv(v, vN.re, U);
@@ -460,6 +491,7 @@ struct BurgersWarp {
         // =============================== epilogue ===============================================
         // A blown-up environment (non-finite / > FLT_MAX spectrum, the reference's FloatingPointError)
         // keeps the state it had before this call and is marked TRUNCATED.
+        for (int it = 0; it < nsub; ++it) tnow += dt;            // t += dt per step (Burger.py:494)
         if (nsub > 0) {
             const bool blew = team_any(f, bad);
             if (was_live && blew && f.dc) prm.status[e] = 1;
@@ -471,7 +503,7 @@ struct BurgersWarp {
                 stcx(prm.v + e * NH + kk[p], v[p]);
                 stcx(prm.fn + e * NH + kk[p], fn[p]);
                 prm.acc[e * NH + kk[p]] = acc32[p];
-                if (prm.version == 1)      // u before the last sub-step: only state version 1 (dudt) reads it
+                if (v1)                    // u before the last sub-step: only state version 1 (dudt) reads it
                     stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
             }
             if (f.dc) {
@@ -484,38 +516,47 @@ struct BurgersWarp {
         }
 
         const T inf = T(1) / T(0);
+        // double-buffered gather (PeerSink): this step's copy of the output buffers
+        const int64_t poff = prm.peer.parity_stride ? (*prm.peer.step & 1) * prm.peer.parity_stride : 0;
+        T* const state_out = prm.state_out ? prm.state_out + poff : nullptr;
+        T* const reward_out = prm.reward_out ? prm.reward_out + poff : nullptr;
         if (prm.state_out && prm.A == 1 && prm.version <= 2) {
             // getState, single agent, versions 0/1/2 (Burger.py:617-622): rows are per-point fields, so the
             // lane's two adjacent points go out as one 16-byte store each -- no shared-memory gather
-            const int ver = prm.version;
+            const int ver = (LEAN && prm.version == 1) ? 0 : prm.version;
             T left[P], right[P];
             halo(f, U, left, right);
             const T sd2 = inv_dx2 * invN, sdt = invN / dt;
             if (has) {
-                Cx<T>* row0 = reinterpret_cast<Cx<T>*>(prm.state_out + e * (ver == 0 ? N : 2 * N));
-                Cx<T>* row1 = row0 + H;
+                const int64_t off = e * (ver == 0 ? N : 2 * N);
                 const Cx<T> ii = cx<T>(inf, inf);
+                // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
+                auto put = [&](int64_t idx, Cx<T> val) {
+                    stcx(reinterpret_cast<Cx<T>*>(state_out + off) + idx, val);
+                    for (int q = 0; q < prm.peer.n_data; ++q)
+                        stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + idx, val);
+                };
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     const int j = p * TS + tl;
                     const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
                     const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2, (U[p].re - T(2) * U[p].im + right[p]) * sd2);
                     if (ver == 0) {
-                        stcx(row0 + j, live ? d2 : ii);
+                        put(j, live ? d2 : ii);
                     } else if (ver == 1) {
                         const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
-                        stcx(row0 + j, live ? dudt : ii);
-                        stcx(row1 + j, live ? d2 : ii);
+                        put(j, live ? dudt : ii);
+                        put(H + j, live ? d2 : ii);
                     } else {
-                        stcx(row0 + j, live ? u : ii);
-                        stcx(row1 + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
+                        put(j, live ? u : ii);
+                        put(H + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
                     }
                 }
             }
         } else if (prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store
-            const int ver = prm.version, A = prm.A;
+            const int ver = (LEAN && prm.version == 1) ? 0 : prm.version, A = prm.A;
             T left[P], right[P];
             halo(f, U, left, right);
             __syncwarp(f.c.tmask);
@@ -557,7 +598,9 @@ struct BurgersWarp {
                     } else {
                         val = f0[2 * N + (r - nf * seg)];
                     }
-                    prm.state_out[e * S + o] = live ? val : inf;          // Burger.py:633-643
+                    const T out = live ? val : inf;                        // Burger.py:633-643
+                    state_out[e * S + o] = out;
+                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.state[q])[poff + e * S + o] = out;
                 }
             }
             __syncwarp(f.c.tmask);
@@ -571,13 +614,17 @@ struct BurgersWarp {
             for (int p = 0; p < P; ++p)
                 if (kk[p] >= 1) {
                     const T es = (T)((double)acc32[p] / (double)(iout + 1));
-                    const T q = fabs(ek_ref[p] - es) / ek_ref[p];
+                    const T er = stash[5 + kk[p]];
+                    const T q = fabs(er - es) / er;
                     part += q * q;
                 }
             part = team_sum(f, part) / T(H - 1);
-            const T r = live ? kprev_old - part : -inf;
+            const T r = live ? stash[4] - part : -inf;
             if (has) {
-                for (int a = tl; a < A; a += TS) prm.reward_out[e * A + a] = r;
+                for (int a = tl; a < A; a += TS) {
+                    reward_out[e * A + a] = r;
+                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
+                }
                 if (f.dc && live) prm.kprev[e] = part;
             }
         }
@@ -601,8 +648,28 @@ struct BurgersWarp {
                 for (int a = tl; a < A; a += TS) {       // agent a owns points [a N/A, (a+1) N/A)
                     T sum = T(0);
                     for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
-                    prm.reward_out[e * A + a] = live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
+                    const T r = live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
+                    reward_out[e * A + a] = r;
+                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
                 }
+            }
+        }
+    }
+
+    // Multi-GPU epilogue (PeerSink): once every CTA's stores are visible system-wide, the last CTA to finish
+    // publishes the step number in slot [my rank] of every rank's flag array.  Called by ALL threads of the CTA.
+    __device__ static void publish(const SpectralParams<T>& prm) {
+        if (prm.peer.n_flags == 0) return;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int done = atomicAdd(prm.peer.ticket, 1u);
+            if (done == gridDim.x - 1) {
+                *prm.peer.ticket = 0;
+                const long long s = *prm.peer.step + 1;
+                *prm.peer.step = s;
+                __threadfence_system();
+                for (int q = 0; q < prm.peer.n_flags; ++q) *reinterpret_cast<volatile long long*>(prm.peer.flags[q]) = s;
             }
         }
     }

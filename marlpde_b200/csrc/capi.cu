@@ -35,6 +35,7 @@ using namespace mpde;
 struct mpde_env {
     mpde_config cfg{};
     int64_t launches = 0;
+    int64_t epoch = 0;      // bumped by every setter: what a step launch looks like may have changed (graph cache key)
     int aux_flags = 0;
     virtual ~mpde_env() {}
     virtual int init() = 0;
@@ -48,6 +49,8 @@ struct mpde_env {
     virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
+    virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int n_flags, void* const* flags,
+                                void* ticket, void* step, int64_t parity_stride) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -84,6 +87,7 @@ struct Env : mpde_env {
         return 0;
     }
     ~Env() override {
+        for (const HostGraph& g : host_graphs) cudaGraphExecDestroy(g.exec);
         for (void* p : owned) cudaFree(p);
     }
 
@@ -264,6 +268,35 @@ struct Env : mpde_env {
         return 0;
     }
 
+    int set_peer_output(int n_data, void* const* state, void* const* reward, int n_flags, void* const* flags, void* ticket,
+                        void* step, int64_t parity_stride) override {
+        if (n_data == 0 && n_flags == 0) {
+            prm.peer = PeerSink{};
+            ++epoch;
+            return 0;
+        }
+        if (cfg.equation != MPDE_BURGERS || cfg.N > 256)
+            return fail("set_peer_output: the fused gather exists for the warp-resident Burgers kernels (N <= 256) only; "
+                        "use mpde_peer_put for the other solvers");
+        if (n_data < 0 || n_data > MAX_PEERS || n_flags < 0 || n_flags > MAX_PEERS) return fail("set_peer_output: at most 8 ranks");
+        if (n_flags > 0 && (!flags || !ticket || !step)) return fail("set_peer_output: flags need ticket and step counters");
+        PeerSink ps;
+        ps.n_data = n_data;
+        ps.n_flags = n_flags;
+        for (int i = 0; i < n_data; ++i) {
+            if (!state || !reward || !state[i] || !reward[i]) return fail("set_peer_output: null peer buffer");
+            ps.state[i] = state[i];
+            ps.reward[i] = reward[i];
+        }
+        for (int i = 0; i < n_flags; ++i) ps.flags[i] = static_cast<long long*>(flags[i]);
+        ps.ticket = static_cast<unsigned int*>(ticket);
+        ps.step = static_cast<long long*>(step);
+        if (parity_stride < 0 || (parity_stride > 0 && !step)) return fail("set_peer_output: double buffering needs the step counter");
+        ps.parity_stride = parity_stride;
+        prm.peer = ps;
+        ++epoch;
+        return 0;
+    }
     int reset(const void* src, bool spectral_ic, const uint8_t* mask, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
         if (!src) return fail("reset: null initial condition");
@@ -311,6 +344,8 @@ struct Env : mpde_env {
         if (nsub == 0) flags |= F_NO_ADVANCE;
         if (aux_flags & 1) flags |= (1 << 8);       // F_KS_UUROW
         p.flags = flags;
+        if ((p.peer.n_data || p.peer.n_flags) && (!state_out || !reward_out || nsub == 0))
+            return fail("step: a fused peer gather is bound (mpde_set_peer_output): every call must advance and write state and reward");
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
             if (cfg.reward_mode == MPDE_REWARD_MSE && !p.truth)
@@ -336,18 +371,66 @@ struct Env : mpde_env {
     // host-buffer variant: stage through library-owned device buffers (allocated on first use)
     T *stage_act = nullptr, *stage_state = nullptr, *stage_reward = nullptr;
     size_t stage_act_n = 0, stage_state_n = 0, stage_reward_n = 0;
-    int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
-        CU(cudaSetDevice(cfg.device));
-        const size_t B = (size_t)cfg.nenvs;
-        const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
-        const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
-        if (na > stage_act_n) { if (dalloc(&stage_act, na)) return -1; stage_act_n = na; }
-        if (ns > stage_state_n) { if (dalloc(&stage_state, ns)) return -1; stage_state_n = ns; }
-        if (nr > stage_reward_n) { if (dalloc(&stage_reward, nr)) return -1; stage_reward_n = nr; }
+    // The chain H2D -> kernel -> D2H of one (actions, nsub, state, reward) signature is captured ONCE into a CUDA
+    // graph and replayed by later calls: one driver call per RL step instead of four (MPDE_HOST_GRAPH=0 disables;
+    // a stream that is already being captured by the caller, or the legacy default stream, gets the plain chain).
+    struct HostGraph {
+        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec;
+    };
+    std::vector<HostGraph> host_graphs;
+    int step_host_enqueue(const void* actions, int nsub, void* state_out, void* reward_out, size_t na, size_t ns, size_t nr,
+                          cudaStream_t st) {
         if (na) CU(cudaMemcpyAsync(stage_act, actions, na * sizeof(T), cudaMemcpyHostToDevice, st));
         if (step(na ? stage_act : nullptr, nsub, ns ? stage_state : nullptr, nr ? stage_reward : nullptr, st)) return -1;
         if (ns) CU(cudaMemcpyAsync(state_out, stage_state, ns * sizeof(T), cudaMemcpyDeviceToHost, st));
         if (nr) CU(cudaMemcpyAsync(reward_out, stage_reward, nr * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (prm.peer.n_data || prm.peer.n_flags)
+            return fail("step_host: a fused peer gather is bound; step with device buffers (mpde_step) and copy the rows out");
+        const size_t B = (size_t)cfg.nenvs;
+        const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
+        const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
+        if (na > stage_act_n) { if (dalloc(&stage_act, na)) return -1; stage_act_n = na; ++epoch; }
+        if (ns > stage_state_n) { if (dalloc(&stage_state, ns)) return -1; stage_state_n = ns; ++epoch; }
+        if (nr > stage_reward_n) { if (dalloc(&stage_reward, nr)) return -1; stage_reward_n = nr; ++epoch; }
+        static const bool use_graph = [] { const char* s = std::getenv("MPDE_HOST_GRAPH"); return !(s && s[0] == '0'); }();
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st) CU(cudaStreamIsCapturing(st, &cs));
+        if (!use_graph || !st || st == cudaStreamLegacy || cs != cudaStreamCaptureStatusNone)
+            return step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
+        for (const HostGraph& g : host_graphs)
+            if (g.actions == actions && g.state == state_out && g.reward == reward_out && g.nsub == nsub && g.epoch == epoch) {
+                CU(cudaGraphLaunch(g.exec, st));
+                launches += g.kernels;
+                return 0;
+            }
+        const int64_t l0 = launches;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
+        const std::string first_err = g_err;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        const int kernels = (int)(launches - l0);
+        launches = l0;
+        if (rc != 0 || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc != 0 ? fail(first_err) : fail(std::string("step_host: graph capture failed: ") + cudaGetErrorString(ce));
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(std::string("step_host: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+        if (host_graphs.size() >= 4) {
+            cudaGraphExecDestroy(host_graphs.front().exec);
+            host_graphs.erase(host_graphs.begin());
+        }
+        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec});
+        CU(cudaGraphLaunch(exec, st));
+        launches += kernels;
         return 0;
     }
 
@@ -474,9 +557,12 @@ int mpde_destroy(mpde_env* env) {
 }
 
 int64_t mpde_state_size(const mpde_env* env) { return env ? env->state_size() : -1; }
-int mpde_set_nu(mpde_env* env, const double* nu, int64_t n) { return env && nu ? env->set_nu(nu, n) : fail("null argument"); }
-int mpde_set_basis(mpde_env* env, int32_t M, const double* b) { return env && b ? env->set_basis(M, b) : fail("null argument"); }
+int mpde_set_nu(mpde_env* env, const double* nu, int64_t n) {
+    if (env) ++env->epoch; return env && nu ? env->set_nu(nu, n) : fail("null argument"); }
+int mpde_set_basis(mpde_env* env, int32_t M, const double* b) {
+    if (env) ++env->epoch; return env && b ? env->set_basis(M, b) : fail("null argument"); }
 int mpde_set_reward_mode(mpde_env* env, int32_t mode) {
+    if (env) ++env->epoch;
     if (!env) return fail("null argument");
     if (mode < 0 || mode > 3) return fail("set_reward_mode: unknown mode");
     env->cfg.reward_mode = mode;
@@ -484,18 +570,23 @@ int mpde_set_reward_mode(mpde_env* env, int32_t mode) {
 }
 int mpde_set_etdrk4(mpde_env* env, const double* E, const double* E2, const double* Q, const double* f1,
                     const double* f2, const double* f3) {
+    if (env) ++env->epoch;
     if (!env || !E || !E2 || !Q || !f1 || !f2 || !f3) return fail("null argument");
     const double* tabs[6] = {E, E2, Q, f1, f2, f3};
     return env->set_etd(tabs);
 }
-int mpde_set_forcing(mpde_env* env, const double* c, int64_t n) { return env && c ? env->set_forcing(c, n) : fail("null argument"); }
+int mpde_set_forcing(mpde_env* env, const double* c, int64_t n) {
+    if (env) ++env->epoch; return env && c ? env->set_forcing(c, n) : fail("null argument"); }
 int mpde_set_spectrum_ref(mpde_env* env, const double* ek, int64_t nref, int64_t rows, const int32_t* map) {
+    if (env) ++env->epoch;
     return env && ek ? env->set_spectrum_ref(ek, nref, rows, map) : fail("null argument");
 }
 int mpde_set_truth(mpde_env* env, const void* t, int64_t nt, int64_t rows, const int32_t* map) {
+    if (env) ++env->epoch;
     return env && t ? env->set_truth(t, nt, rows, map) : fail("null argument");
 }
 int mpde_set_history(mpde_env* env, void* uu, void* vv, double* ektt, int64_t rows) {
+    if (env) ++env->epoch;
     return env ? env->set_history(uu, vv, ektt, rows) : fail("null argument");
 }
 int mpde_reset_u(mpde_env* env, const void* u0, const uint8_t* mask, void* stream) {
@@ -510,6 +601,12 @@ int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out,
 int mpde_step_host(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step_host(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
+int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int32_t n_flags,
+                         void* const* flag_ptrs, void* ticket_dev, void* step_dev, int64_t parity_stride) {
+    if (env) ++env->epoch;
+    return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, n_flags, flag_ptrs, ticket_dev, step_dev, parity_stride)
+               : fail("null argument");
+}
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
@@ -517,6 +614,7 @@ int mpde_set(mpde_env* env, int32_t field, const void* src, void* stream) {
     return env && src ? env->set(field, src, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
 int mpde_set_option(mpde_env* env, int32_t key, int64_t value) {
+    if (env) ++env->epoch;
     if (!env) return fail("null argument");
     if (key == MPDE_OPT_KS_UUROW) {
         env->aux_flags = (env->aux_flags & ~1) | (value ? 1 : 0);

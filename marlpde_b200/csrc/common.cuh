@@ -52,6 +52,12 @@ template <typename T> __device__ __forceinline__ bool blown(Cx<T> v) {
     return !(fabs((double)v.re) <= (double)FLT_MAX && fabs((double)v.im) <= (double)FLT_MAX);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still running; it must not touch memory the predecessor
+// writes before pdl_wait() returns (= predecessor complete and flushed).  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
 }  // namespace mpde

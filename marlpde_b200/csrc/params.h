@@ -19,6 +19,24 @@ enum : int {
 enum : int { REWARD_NONE = 0, REWARD_SPECTRAL = 1, REWARD_MSE = 2, REWARD_DIRECT = 3 };
 enum : int { AUX_RESET_U = 0, AUX_RESET_V = 1, AUX_GET_U = 2 };
 
+// Multi-GPU gather fused into the step kernel's epilogue: besides state_out / reward_out (this rank's slab in its
+// own gather buffer) every state / reward store is repeated into this rank's slab of each peer's gather buffer
+// (peer-mapped pointers, plain stores over NVLink).  The last CTA to finish publishes a step number in
+// slot [my rank] of every rank's flag array.
+constexpr int MAX_PEERS = 8;
+struct PeerSink {
+    int n_data = 0;                 // peers that receive a copy of the outputs (other ranks)
+    int n_flags = 0;                // flag slots to publish (all ranks, this one included)
+    void* state[MAX_PEERS] = {};    // peer p: where this rank's [B,S] state slab lives in p's gather buffer
+    void* reward[MAX_PEERS] = {};   // peer p: where this rank's [B,A] reward slab lives
+    long long* flags[MAX_PEERS] = {};  // rank p: &flag_array_of_p[my rank]
+    unsigned int* ticket = nullptr; // device counter: CTAs finished so far
+    long long* step = nullptr;      // device counter: steps published so far
+    long long parity_stride = 0;    // elements of T between the two copies of every gather buffer (0 = single-buffered):
+                                    // step s (0-based) writes copy s & 1, locally and on the peers, so a fast rank never
+                                    // overwrites rows a slow rank's learner is still reading
+};
+
 template <typename T>
 struct SpectralParams {
     int64_t B;
@@ -58,6 +76,7 @@ struct SpectralParams {
     Cx<float>* vv_hist;     // [B][hist_rows][N] complex64, FFT order
     double* ektt_hist;      // [B][hist_rows][N/2+1] running time-average of the spectrum (Ek_ktt)
     int64_t hist_rows;
+    PeerSink peer;
 };
 
 }  // namespace mpde

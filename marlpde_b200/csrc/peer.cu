@@ -61,6 +61,27 @@ __global__ void peer_wait_kernel(const long long* flags, int nranks, long long s
     }
     __threadfence_system();
 }
+// consumer side of the fused gather: the expected step lives on the device (CUDA-graph replayable)
+__global__ void peer_wait_next_kernel(const long long* flags, int nranks, long long* expect, int* err, long long max_spins) {
+    __shared__ long long want;
+    if (threadIdx.x == 0) want = *expect + 1;
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const volatile long long* f = flags + r;
+        long long spins = 0;
+        while (*f < want) {
+            if (++spins > max_spins) {
+                atomicExch(err, 1 + r);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *expect = want;
+    __threadfence_system();
+}
 }  // namespace
 
 extern "C" {
@@ -117,6 +138,15 @@ int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void*
     if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait: 1..16 ranks");
     peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks, (long long)step,
                                                                       static_cast<int*>(err_dev), (long long)max_spins);
+    PCU(cudaGetLastError());
+    return 0;
+}
+
+int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream) {
+    if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait_next: 1..16 ranks");
+    peer_wait_next_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks,
+                                                                           static_cast<long long*>(expect_dev),
+                                                                           static_cast<int*>(err_dev), (long long)max_spins);
     PCU(cudaGetLastError());
     return 0;
 }

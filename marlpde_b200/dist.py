@@ -70,9 +70,13 @@ class PeerGather:
     put(src)  : enqueue the copy of this rank's slab into every rank's ``gathered[rank]`` + publish the step
     wait()    : make the current stream wait until every rank's slab of the current step has landed here
     gathered  : [world_size, chunk_elems] tensor living in this rank's exported buffer
+
+    Fused mode (``copies=2`` + ``fuse(env, ...)``): the Burgers step kernel itself stores state and reward into every
+    rank's buffer and publishes the step (include/marlpde_b200.h, mpde_set_peer_output); ``wait_next()`` is the
+    consumer side and ``current()`` the [world_size, chunk_elems] copy the last step wrote (double-buffered).
     """
 
-    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24):
+    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24, copies=1):
         import ctypes as C
         from . import _lib as LB
         self._C, self._lib = C, LB.lib()
@@ -81,7 +85,9 @@ class PeerGather:
         item = torch.empty((), dtype=dtype).element_size()
         self.chunk_bytes = (chunk_elems * item + 15) // 16 * 16
         self.chunk_elems, self.dtype, self.max_spins = chunk_elems, dtype, int(max_spins)
-        gbytes = self.ws * self.chunk_bytes
+        self.copies = int(copies)
+        self._copy_bytes = self.ws * self.chunk_bytes
+        gbytes = self.copies * self._copy_bytes
         total = gbytes + 16 * ((self.ws * 8 + 15) // 16)
         base = C.c_void_p()
         self._check(self._lib.mpde_peer_alloc(total, C.byref(base)))
@@ -106,7 +112,11 @@ class PeerGather:
         self._flags = arr(*[b + gbytes for b in self._peer_bases])
         self._my_flags = self._base + gbytes
         raw = torch.as_tensor(_RawDeviceMemory(self._base, gbytes), device=self.device)
-        self.gathered = raw.view(self.ws, self.chunk_bytes).view(dtype)[:, :chunk_elems]
+        self._all = raw.view(self.copies, self.ws, self.chunk_bytes).view(dtype)[:, :, :chunk_elems]
+        self.gathered = self._all[0]
+        self._item = item
+        self._steps_dev = torch.zeros(4, dtype=torch.int64, device=self.device)    # [0] published, [1] awaited
+        self._fused = None
         self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._err = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.step = 0
@@ -131,6 +141,37 @@ class PeerGather:
         self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err.data_ptr(), self.max_spins,
                                              self._stream()))
 
+    def fuse(self, env, n_local, S, A):
+        """Let ``env``'s step kernel write its [n_local,S] state and [n_local,A] reward straight into this rank's slab
+        of every rank's buffer and publish the step itself (no put kernel, no NCCL)."""
+        C = self._C
+        assert n_local * (S + A) == self.chunk_elems
+        slab = self.rank * self.chunk_bytes
+        mine = self._all[0, self.rank]
+        env.bind_output(mine[:n_local * S].view(n_local, S), mine[n_local * S:].view(n_local, A))
+        others = [r for r in range(self.ws) if r != self.rank]
+        arr_o = C.c_void_p * max(1, len(others))
+        st = arr_o(*[self._peer_bases[r] + slab for r in others])
+        rw = arr_o(*[self._peer_bases[r] + slab + n_local * S * self._item for r in others])
+        arr_f = C.c_void_p * self.ws
+        fl = arr_f(*[self._peer_bases[r] + self.copies * self._copy_bytes + 8 * self.rank for r in range(self.ws)])
+        stride = self._copy_bytes // self._item if self.copies == 2 else 0
+        rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, self.ws, fl, self._counter.data_ptr(),
+                                            self._steps_dev.data_ptr(), stride)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
+        self._fused = env
+        env._state_at = env._reward_at = -1
+
+    def wait_next(self):
+        """Current stream waits until every rank has published one more step than the last wait_next() saw."""
+        self._check(self._lib.mpde_peer_wait_next(self._my_flags, self.ws, self._steps_dev[1:].data_ptr(), self._err.data_ptr(),
+                                                  self.max_spins, self._stream()))
+
+    def current(self):
+        """[world_size, chunk_elems] copy written by step number ``self.step`` (1-based host count of fused steps)."""
+        return self._all[(self.step - 1) & 1] if self.copies == 2 else self._all[0]
+
     def check(self):
         e = int(self._err[0])
         if e:
@@ -139,6 +180,9 @@ class PeerGather:
     def close(self):
         if getattr(self, "_base", None):
             torch.cuda.synchronize(self.device)
+            if self._fused is not None:
+                self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0, None, None, None, 0)
+                self._fused = None
             if self.ws > 1:
                 dist.barrier()
             for p in self._opened:
@@ -171,7 +215,12 @@ class ShardedBatch:
             buf = self.env._state_buf
             self._flat = torch.zeros(nl * (S + A), dtype=buf.dtype, device=buf.device)
             self.env.bind_output(self._flat[:nl * S].view(nl, S), self._flat[nl * S:].view(nl, A))
-            if transport == "p2p":
+            if transport == "fused":
+                # the step kernel writes straight into every rank's (double-buffered) gather buffer
+                self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device, copies=2)
+                self._peer.fuse(self.env, nl, S, A)
+                self._gflat = self._peer.gathered
+            elif transport == "p2p":
                 self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device)
                 self._gflat = self._peer.gathered
             else:
@@ -185,7 +234,10 @@ class ShardedBatch:
 
     def wait(self):
         """Block the current stream until the last asynchronous gather has landed."""
-        if self._work == "p2p":
+        if self._work == "fused":
+            self._peer.wait_next()
+            self._work = None
+        elif self._work == "p2p":
             self._peer.wait()
             self._work = None
         elif self._work is not None:
@@ -195,7 +247,7 @@ class ShardedBatch:
     def views(self):
         """(states [R, B/R, S], rewards [R, B/R, A]) views of the gathered buffer, global env order."""
         nl = self.hi - self.lo
-        g = self._gflat
+        g = self._peer.current() if self.transport == "fused" else self._gflat
         return g[:, :nl * self._S].view(self.world_size, nl, self._S), g[:, nl * self._S:].view(self.world_size, nl, self._A)
 
     def step_n(self, actions_global_or_local, n=1, async_gather=False, **kw):
@@ -205,7 +257,12 @@ class ShardedBatch:
         self.wait()                                   # the send buffer is about to be overwritten
         st, rw = self.env.step_n(a, n, **kw)
         if self._flat is not None and st is not None and rw is not None:
-            if self._peer is not None:
+            if self.transport == "fused":
+                self._peer.step += 1
+                self._work = "fused"
+                if not async_gather:
+                    self.wait()
+            elif self._peer is not None:
                 self._peer.put(self._flat)
                 self._work = "p2p"
                 if not async_gather:

@@ -41,7 +41,9 @@ class HostPipeline:
                 self.act_dev[k].copy_(self.act_host[k], non_blocking=True)
                 st, rw = self.envs[k].step_n(self.act_dev[k], self.n_sub)
                 if self.post_step is not None:
-                    self.post_step(k, st, rw)
+                    res = self.post_step(k, st, rw)       # may return the (state, reward) tensors to copy out instead
+                    if res is not None:
+                        st, rw = res
                 self.state_host[k].copy_(st, non_blocking=True)
                 if rw is not None:
                     self.reward_host[k].copy_(rw, non_blocking=True)

@@ -37,20 +37,20 @@ def _worker(rank, ws, port, q, transport="nccl"):
         for _ in range(3):
             gs, gr = sb.step_n(a, 10)
         torch.cuda.synchronize()
-        if transport == "p2p":
+        if transport in ("p2p", "fused"):
             sb._peer.check()
         q.put((rank, gs.cpu().numpy(), gr.cpu().numpy()))
-        if transport == "p2p":
+        if transport in ("p2p", "fused"):
             sb._peer.close()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused"])
 def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     import torch.multiprocessing as mp
-    ws, port = 2, 29500 + os.getpid() % 400 + (50 if transport == "p2p" else 0)
+    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100}[transport]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q, transport)) for r in range(ws)]
@@ -81,3 +81,42 @@ def test_peer_gather_single_rank_roundtrip():
         pg.check()
         assert torch.equal(pg.gathered[0], x + k)
     pg.close()
+
+
+def test_fused_gather_single_rank_matches_plain_step():
+    """transport="fused" on one GPU: the step kernel writes into the (double-buffered) gather buffer and publishes the
+    step itself; results equal the plain step_n of an identical batch, bitwise, over odd and even steps."""
+    from marlpde_b200 import dist as mdist
+    torch.cuda.set_device(0)
+    sb = mdist.ShardedBatch(B, _factory, transport="fused")
+    ref = _factory(B, np.arange(B))
+    a = _acts().cuda()
+    for k in range(5):
+        gs, gr = sb.step_n(a, 7)
+        st, rw = ref.step_n(a, 7)
+        torch.cuda.synchronize()
+        sb._peer.check()
+        assert torch.equal(gs, st) and torch.equal(gr, rw), k
+    assert int(sb._peer._steps_dev[0]) == 5 and int(sb._peer._steps_dev[1]) == 5
+    sb._peer.close()
+
+
+def test_host_step_graph_replay_matches_plain_chain():
+    """mpde_step_host replays a cached CUDA graph (H2D -> kernel -> D2H) after its first call on a stream: same bits
+    as the device-buffer path."""
+    torch.cuda.set_device(0)
+    env, ref = _factory(B, np.arange(B)), _factory(B, np.arange(B))
+    a_host = _acts().pin_memory()
+    a_dev = a_host.cuda()
+    S = env._state_buf.shape[1]
+    st_h = torch.empty((B, S), dtype=torch.float64).pin_memory()
+    rw_h = torch.empty((B, 1), dtype=torch.float64).pin_memory()
+    stream = torch.cuda.Stream()
+    l0 = env.launch_count
+    for k in range(4):
+        env.step_n_host(a_host, 10, st_h, rw_h, stream=stream)
+        stream.synchronize()
+        st, rw = ref.step_n(a_dev, 10)
+        torch.cuda.synchronize()
+        assert torch.equal(st_h, st.cpu()) and torch.equal(rw_h, rw.cpu()), k
+    assert env.launch_count - l0 == 4

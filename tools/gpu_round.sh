@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU-box visit: GPU test suite, default bench (both arms), team-size sweep, ncu launch list + full capture.
+# usage (from the repo root, under gpurun):  bash tools/gpu_round.sh <tag>
+set -u
+tag=${1:-r1}
+out=gpurun_out
+mkdir -p $out
+python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log
+tail -3 $out/${tag}_pytest.log
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 40 --warmup 3 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; echo "ref rc=$?"
+for ts in 16 8 4; do
+  MPDE_TS=$ts python bench.py --steps 1000 --warmup 20 --no-cpu > $out/${tag}_bench_ts$ts.json 2>> $out/${tag}_bench.err
+done
+python bench.py --steps 60 --warmup 5 --no-cpu --pool 4 > $out/${tag}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 60 --warmup 5 --no-cpu --pool 4 > $out/${tag}_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:burgers_warp -s 20 -c 3 -f -o $out/${tag}_prof_burgers \
+    python bench.py --steps 60 --warmup 5 --no-cpu --pool 4 > $out/${tag}_ncu2.log 2>&1
+echo done
