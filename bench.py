@@ -193,7 +193,8 @@ def gpu_arm(args):
     acts = acts_host.to(device)
     S = envs[0]._state_size
     gathers = []
-    if world > 1:
+    fused = world > 1 or args.fused_single      # --fused-single: 1-GPU diagnostic of the fused-gather overheads
+    if fused:
         # Learner-side gather FUSED into the step kernel: every rank's kernel stores its state + reward rows straight
         # into every rank's (double-buffered) gather buffer over NVLink and publishes a step flag; a 1-CTA wait kernel
         # is the consumer side.  No NCCL call and no host work per step (marlpde_b200.dist.PeerGather.fuse).
@@ -203,12 +204,22 @@ def gpu_arm(args):
             pg.fuse(env, B_PER_GPU, S, 1)
             gathers.append(pg)
 
-    def one_step(i):
+    side = torch.cuda.Stream(device=device) if fused else None
+
+    def one_step(i, join=True):
         k = i % pool
         st, rw = envs[k].step_n(acts[k], NSUB)
-        if world > 1:
+        if fused and not args.no_wait:
+            # consumer side of the gather (all ranks' rows of this step have landed in this rank's buffer): it orders
+            # the LEARNER after the step, not the next batch's step kernel, so it runs on a forked stream and the
+            # step kernels stay back to back (programmatic dependent launch); joined once per rotation / step
+            main = torch.cuda.current_stream()
             gathers[k].step += 1
-            gathers[k].wait_next()          # all ranks' rows of this step have landed in this rank's buffer
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                gathers[k].exchange_next()  # behind the kernel boundary: publish this rank's rows, wait for the peers' 
+            if join:
+                main.wait_stream(side)
         return st, rw
 
     def drain():
@@ -222,39 +233,41 @@ def gpu_arm(args):
     # The pool rotation (one RL step of each of the `pool` batches) is captured once into a CUDA graph and replayed:
     # the launch loop is host-bound otherwise (~14 us of Python per step_n call vs a ~16 us kernel).
     graph, per_graph = None, 0
+    rot = pool * (2 if fused else 1)        # steps per graph: both copies of the double-buffered gather when fused
+    extra = 1 if fused and not args.no_wait else 0      # signal+wait kernel per step
     if args.graph:
-        for i in range(pool):               # warm every batch before capture
+        for i in range(rot):                # warm every batch before capture
             one_step(i)
         sync()
         l_before = sum(e.launch_count for e in envs)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for i in range(pool):
-                one_step(i)
-        per_graph = (sum(e.launch_count for e in envs) - l_before) + (pool if world > 1 else 0)
+            for i in range(rot):
+                one_step(i, join=(i == rot - 1))
+        per_graph = (sum(e.launch_count for e in envs) - l_before) + extra * rot
         for g in gathers:                   # the capture pass only recorded: no step was published
-            g.step -= 1
+            g.step -= rot // pool
         torch.cuda.synchronize()
 
     def run_steps(first, n):
         """n RL steps starting at rotation index `first` (a multiple of pool when the graph is used)."""
         launched = 0
         if graph is not None:
-            reps, n = divmod(n, pool)
+            reps, n = divmod(n, rot)
             for _ in range(reps):
                 graph.replay()
             launched += reps * per_graph
             for g in gathers:
-                g.step += reps
-            first += reps * pool
+                g.step += reps * (rot // pool)
+            first += reps * rot
         l0 = sum(e.launch_count for e in envs)
         for i in range(n):
             one_step(first + i)
-        launched += sum(e.launch_count for e in envs) - l0 + (n if world > 1 else 0)
+        launched += sum(e.launch_count for e in envs) - l0 + extra * n
         return launched
 
     sampler = ClockSampler(local) if rank == 0 else None      # covers warm-up + timed + e2e regions
-    Wr = -(-W // pool) * pool if graph is not None else W      # whole rotations keep the graph aligned
+    Wr = -(-W // rot) * rot if graph is not None else W        # whole rotations keep the graph aligned
     run_steps(0, Wr)
     sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,11 +292,11 @@ def gpu_arm(args):
     def gather(k, st, rw):            # N > 1: the fused gather stays part of every step; copy out this step's rows
         g = gathers[k]
         g.step += 1
-        g.wait_next()
+        g.exchange_next()
         mine = g.current()[rank]
         return mine[:B_PER_GPU * S].view(B_PER_GPU, S), mine[B_PER_GPU * S:].view(B_PER_GPU, 1)
 
-    pipe = HostPipeline(envs[:depth], NSUB, post_step=gather if world > 1 else None)
+    pipe = HostPipeline(envs[:depth], NSUB, post_step=gather if fused else None)
     for k in range(depth):
         pipe.act_host[k].copy_(acts_host[k])
     Ke = max(depth, min(K, 2000))
@@ -358,6 +371,8 @@ def main():
     ap.add_argument("--depth", type=int, default=4, help="e2e: independent batches in flight")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")
+    ap.add_argument("--no-wait", action="store_true", help="diagnostic: skip the consumer-side wait kernels")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of "
                     "replaying the captured pool rotation")
     args = ap.parse_args()

@@ -185,17 +185,21 @@ const char* mpde_peer_last_error(void);
 /* Gather FUSED into the step kernel (warp-resident Burgers kernels, N <= 256): after this call every mpde_step of
  * `env` repeats its state / reward stores into `state_ptrs[i]` / `reward_ptrs[i]` (i < n_data: this rank's slab inside
  * the gather buffer of every OTHER rank, peer-mapped through mpde_peer_open; the local slab is the state_out /
- * reward_out of the call) and, when its last CTA has finished, publishes ++(*step_dev) to the n_flags addresses
- * `flag_ptrs[j]` (= &flag_array_of_rank_j[my rank], this rank included).  ticket_dev (uint32) and step_dev (int64) are
- * zero-initialised device words owned by the caller, one pair per env.  n_data = n_flags = 0 unbinds.
- * parity_stride > 0 double-buffers: step s (0-based count in *step_dev) writes every buffer -- the local state_out /
- * reward_out included -- at an offset of (s & 1) * parity_stride ELEMENTS, so a fast rank's next step never lands in
- * rows a slower rank's learner is still reading.
- * mpde_peer_wait_next is the consumer side: the stream waits until every slot of this rank's flag array has reached
- * ++(*expect_dev) -- all counters live on the device, so step + wait can be replayed from a CUDA graph. */
-int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int32_t n_flags,
-                         void* const* flag_ptrs, void* ticket_dev, void* step_dev, int64_t parity_stride);
+ * reward_out of the call).  parity_stride > 0 double-buffers: the s-th step enqueued since this call (0-based, counted
+ * by the library on the host) writes every buffer -- the local state_out / reward_out included -- at an offset of
+ * (s & 1) * parity_stride ELEMENTS, so a fast rank's next step never lands in rows a slower rank's learner is still
+ * reading (a CUDA graph that replays steps of `env` must therefore hold an even number of them).
+ * n_data = 0 and parity_stride = 0 unbinds.
+ * Publishing is stream-ordered behind the step: mpde_peer_signal_next bumps *step_dev (int64, device) and stores it to
+ * the n addresses flag_ptrs[j] = &flag_array_of_rank_j[my rank] (this rank included); mpde_peer_wait_next makes the
+ * stream wait until every slot of this rank's flag array has reached ++(*expect_dev).  All counters live on the device,
+ * so step + signal + wait replay from a CUDA graph; neither needs to sit on the step kernels' own stream. */
+int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride);
+int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream);
 int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
+/* signal_next + wait_next as ONE kernel launch */
+int mpde_peer_exchange_next(void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
+                            void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
 
 const char* mpde_last_error(void);
 int mpde_abi_version(void);

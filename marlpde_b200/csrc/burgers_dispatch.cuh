@@ -25,7 +25,6 @@ template <typename T, int N, int TS, int SF, bool LEAN>
 __global__ void __launch_bounds__(MPDE_LB) burgers_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BurgersWarp<T, N, TS, SF, LEAN>::run(prm, reinterpret_cast<T*>(smem_raw));
-    BurgersWarp<T, N, TS, SF, LEAN>::publish(prm);
 }
 
 template <typename T, int N, int TS, int SF, bool LEAN = false>

@@ -83,7 +83,7 @@ struct BurgersWarp {
         const int warp = threadIdx.x >> 5;
         const int wpc = blockDim.x >> 5;
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
-        if (first >= prm.B) return;                                  // whole warp idle (publish() still runs in the kernel)
+        if (first >= prm.B) return;                                  // whole warp idle 
         R f;
         f.init(prm.tw);
         const int tl = f.c.tl;
@@ -517,7 +517,7 @@ struct BurgersWarp {
 
         const T inf = T(1) / T(0);
         // double-buffered gather (PeerSink): this step's copy of the output buffers
-        const int64_t poff = prm.peer.parity_stride ? (*prm.peer.step & 1) * prm.peer.parity_stride : 0;
+        const int64_t poff = prm.peer.parity * prm.peer.parity_stride;
         T* const state_out = prm.state_out ? prm.state_out + poff : nullptr;
         T* const reward_out = prm.reward_out ? prm.reward_out + poff : nullptr;
         if (prm.state_out && prm.A == 1 && prm.version <= 2) {
@@ -652,24 +652,6 @@ struct BurgersWarp {
                     reward_out[e * A + a] = r;
                     for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
                 }
-            }
-        }
-    }
-
-    // Multi-GPU epilogue (PeerSink): once every CTA's stores are visible system-wide, the last CTA to finish
-    // publishes the step number in slot [my rank] of every rank's flag array.  Called by ALL threads of the CTA.
-    __device__ static void publish(const SpectralParams<T>& prm) {
-        if (prm.peer.n_flags == 0) return;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int done = atomicAdd(prm.peer.ticket, 1u);
-            if (done == gridDim.x - 1) {
-                *prm.peer.ticket = 0;
-                const long long s = *prm.peer.step + 1;
-                *prm.peer.step = s;
-                __threadfence_system();
-                for (int q = 0; q < prm.peer.n_flags; ++q) *reinterpret_cast<volatile long long*>(prm.peer.flags[q]) = s;
             }
         }
     }

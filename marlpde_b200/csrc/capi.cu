@@ -49,8 +49,7 @@ struct mpde_env {
     virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
-    virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int n_flags, void* const* flags,
-                                void* ticket, void* step, int64_t parity_stride) = 0;
+    virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -268,35 +267,31 @@ struct Env : mpde_env {
         return 0;
     }
 
-    int set_peer_output(int n_data, void* const* state, void* const* reward, int n_flags, void* const* flags, void* ticket,
-                        void* step, int64_t parity_stride) override {
-        if (n_data == 0 && n_flags == 0) {
-            prm.peer = PeerSink{};
-            ++epoch;
-            return 0;
-        }
+    int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride) override {
+        peer_bound = false;
+        peer_steps = 0;
+        prm.peer = PeerSink{};
+        if (n_data == 0 && parity_stride == 0) return 0;
         if (cfg.equation != MPDE_BURGERS || cfg.N > 256)
             return fail("set_peer_output: the fused gather exists for the warp-resident Burgers kernels (N <= 256) only; "
                         "use mpde_peer_put for the other solvers");
-        if (n_data < 0 || n_data > MAX_PEERS || n_flags < 0 || n_flags > MAX_PEERS) return fail("set_peer_output: at most 8 ranks");
-        if (n_flags > 0 && (!flags || !ticket || !step)) return fail("set_peer_output: flags need ticket and step counters");
+        if (n_data < 0 || n_data > MAX_PEERS) return fail("set_peer_output: at most 8 peers");
+        if (parity_stride < 0) return fail("set_peer_output: negative parity_stride");
         PeerSink ps;
         ps.n_data = n_data;
-        ps.n_flags = n_flags;
         for (int i = 0; i < n_data; ++i) {
             if (!state || !reward || !state[i] || !reward[i]) return fail("set_peer_output: null peer buffer");
             ps.state[i] = state[i];
             ps.reward[i] = reward[i];
         }
-        for (int i = 0; i < n_flags; ++i) ps.flags[i] = static_cast<long long*>(flags[i]);
-        ps.ticket = static_cast<unsigned int*>(ticket);
-        ps.step = static_cast<long long*>(step);
-        if (parity_stride < 0 || (parity_stride > 0 && !step)) return fail("set_peer_output: double buffering needs the step counter");
         ps.parity_stride = parity_stride;
         prm.peer = ps;
-        ++epoch;
+        peer_bound = true;
         return 0;
     }
+    bool peer_bound = false;
+    int64_t peer_steps = 0;     // steps enqueued since the gather was bound: its low bit selects the buffer copy
+
     int reset(const void* src, bool spectral_ic, const uint8_t* mask, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
         if (!src) return fail("reset: null initial condition");
@@ -344,8 +339,12 @@ struct Env : mpde_env {
         if (nsub == 0) flags |= F_NO_ADVANCE;
         if (aux_flags & 1) flags |= (1 << 8);       // F_KS_UUROW
         p.flags = flags;
-        if ((p.peer.n_data || p.peer.n_flags) && (!state_out || !reward_out || nsub == 0))
-            return fail("step: a fused peer gather is bound (mpde_set_peer_output): every call must advance and write state and reward");
+        if (peer_bound) {
+            if (!state_out || !reward_out || nsub == 0)
+                return fail("step: a fused peer gather is bound (mpde_set_peer_output): every call must advance and write state and reward");
+            p.peer.parity = (int)(peer_steps & 1);
+            ++peer_steps;
+        }
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
             if (cfg.reward_mode == MPDE_REWARD_MSE && !p.truth)
@@ -388,7 +387,7 @@ struct Env : mpde_env {
     }
     int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
-        if (prm.peer.n_data || prm.peer.n_flags)
+        if (peer_bound)
             return fail("step_host: a fused peer gather is bound; step with device buffers (mpde_step) and copy the rows out");
         const size_t B = (size_t)cfg.nenvs;
         const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
@@ -601,11 +600,9 @@ int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out,
 int mpde_step_host(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step_host(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
-int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int32_t n_flags,
-                         void* const* flag_ptrs, void* ticket_dev, void* step_dev, int64_t parity_stride) {
+int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride) {
     if (env) ++env->epoch;
-    return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, n_flags, flag_ptrs, ticket_dev, step_dev, parity_stride)
-               : fail("null argument");
+    return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, parity_stride) : fail("null argument");
 }
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");

@@ -21,20 +21,18 @@ enum : int { AUX_RESET_U = 0, AUX_RESET_V = 1, AUX_GET_U = 2 };
 
 // Multi-GPU gather fused into the step kernel's epilogue: besides state_out / reward_out (this rank's slab in its
 // own gather buffer) every state / reward store is repeated into this rank's slab of each peer's gather buffer
-// (peer-mapped pointers, plain stores over NVLink).  The last CTA to finish publishes a step number in
-// slot [my rank] of every rank's flag array.
+// (peer-mapped pointers, plain stores over NVLink).  Publishing the step to the peers is NOT done here: a
+// system-scope fence in this kernel costs ~6 us on B200, so a 1-thread signal kernel behind the kernel boundary
+// (peer.cu) does it off the critical path.
 constexpr int MAX_PEERS = 8;
 struct PeerSink {
     int n_data = 0;                 // peers that receive a copy of the outputs (other ranks)
-    int n_flags = 0;                // flag slots to publish (all ranks, this one included)
+    int parity = 0;                 // which copy of the double-buffered gather buffers this launch writes
+    long long parity_stride = 0;    // elements of T between the two copies (0 = single-buffered): step s writes copy
+                                    // s & 1, locally and on the peers, so a fast rank never overwrites rows a slow
+                                    // rank's learner is still reading
     void* state[MAX_PEERS] = {};    // peer p: where this rank's [B,S] state slab lives in p's gather buffer
     void* reward[MAX_PEERS] = {};   // peer p: where this rank's [B,A] reward slab lives
-    long long* flags[MAX_PEERS] = {};  // rank p: &flag_array_of_p[my rank]
-    unsigned int* ticket = nullptr; // device counter: CTAs finished so far
-    long long* step = nullptr;      // device counter: steps published so far
-    long long parity_stride = 0;    // elements of T between the two copies of every gather buffer (0 = single-buffered):
-                                    // step s (0-based) writes copy s & 1, locally and on the peers, so a fast rank never
-                                    // overwrites rows a slow rank's learner is still reading
 };
 
 template <typename T>

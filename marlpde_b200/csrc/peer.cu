@@ -61,10 +61,50 @@ __global__ void peer_wait_kernel(const long long* flags, int nranks, long long s
     }
     __threadfence_system();
 }
+// producer side of the fused gather: runs BEHIND the step kernel in stream order (the kernel boundary makes the step
+// kernel's peer stores visible), bumps the device-side step counter and publishes it in slot [my rank] of every
+// rank's flag array.  One thread: its system-scope fence has nothing outstanding to wait for.
+struct FlagTable { long long* f[MAX_RANKS]; };
+__global__ void peer_signal_next_kernel(FlagTable tab, int n, long long* step) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const long long s = *step + 1;
+        *step = s;
+        __threadfence_system();
+        for (int q = 0; q < n; ++q) *reinterpret_cast<volatile long long*>(tab.f[q]) = s;
+    }
+}
 // consumer side of the fused gather: the expected step lives on the device (CUDA-graph replayable)
 __global__ void peer_wait_next_kernel(const long long* flags, int nranks, long long* expect, int* err, long long max_spins) {
     __shared__ long long want;
     if (threadIdx.x == 0) want = *expect + 1;
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        const volatile long long* f = flags + r;
+        long long spins = 0;
+        while (*f < want) {
+            if (++spins > max_spins) {
+                atomicExch(err, 1 + r);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *expect = want;
+    __threadfence_system();
+}
+// signal + wait in one launch (what a symmetric learner loop does after every step)
+__global__ void peer_exchange_next_kernel(FlagTable tab, int n, long long* step, const long long* flags, int nranks, long long* expect,
+                                          int* err, long long max_spins) {
+    __shared__ long long want;
+    if (threadIdx.x == 0) {
+        const long long s = *step + 1;
+        *step = s;
+        __threadfence_system();
+        for (int q = 0; q < n; ++q) *reinterpret_cast<volatile long long*>(tab.f[q]) = s;
+        want = *expect + 1;
+    }
     __syncthreads();
     const int r = threadIdx.x;
     if (r < nranks) {
@@ -138,6 +178,28 @@ int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void*
     if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait: 1..16 ranks");
     peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks, (long long)step,
                                                                       static_cast<int*>(err_dev), (long long)max_spins);
+    PCU(cudaGetLastError());
+    return 0;
+}
+
+int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream) {
+    if (n < 1 || n > MAX_RANKS || !flag_ptrs || !step_dev) return pfail("peer_signal_next: 1..16 flag slots and a step counter");
+    FlagTable tab;
+    for (int q = 0; q < n; ++q) tab.f[q] = static_cast<long long*>(flag_ptrs[q]);
+    peer_signal_next_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(tab, n, static_cast<long long*>(step_dev));
+    PCU(cudaGetLastError());
+    return 0;
+}
+
+int mpde_peer_exchange_next(void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
+                            void* expect_dev, void* err_dev, int64_t max_spins, void* stream) {
+    if (n < 1 || n > MAX_RANKS || nranks < 1 || nranks > MAX_RANKS || !flag_ptrs || !step_dev || !expect_dev)
+        return pfail("peer_exchange_next: 1..16 ranks, flag slots and both counters");
+    FlagTable tab;
+    for (int q = 0; q < n; ++q) tab.f[q] = static_cast<long long*>(flag_ptrs[q]);
+    peer_exchange_next_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        tab, n, static_cast<long long*>(step_dev), static_cast<const long long*>(my_flags_dev), nranks,
+        static_cast<long long*>(expect_dev), static_cast<int*>(err_dev), (long long)max_spins);
     PCU(cudaGetLastError());
     return 0;
 }

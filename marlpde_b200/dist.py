@@ -154,14 +154,23 @@ class PeerGather:
         st = arr_o(*[self._peer_bases[r] + slab for r in others])
         rw = arr_o(*[self._peer_bases[r] + slab + n_local * S * self._item for r in others])
         arr_f = C.c_void_p * self.ws
-        fl = arr_f(*[self._peer_bases[r] + self.copies * self._copy_bytes + 8 * self.rank for r in range(self.ws)])
+        self._flag_slots = arr_f(*[self._peer_bases[r] + self.copies * self._copy_bytes + 8 * self.rank for r in range(self.ws)])
         stride = self._copy_bytes // self._item if self.copies == 2 else 0
-        rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, self.ws, fl, self._counter.data_ptr(),
-                                            self._steps_dev.data_ptr(), stride)
+        rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, stride)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         self._fused = env
         env._state_at = env._reward_at = -1
+
+    def signal_next(self):
+        """Enqueue (behind the step kernel in stream order) the publication of one more step to every rank."""
+        self._check(self._lib.mpde_peer_signal_next(self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._stream()))
+
+    def exchange_next(self):
+        """signal_next() + wait_next() as one kernel launch."""
+        self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._my_flags, self.ws,
+                                                      self._steps_dev[1:].data_ptr(), self._err.data_ptr(), self.max_spins,
+                                                      self._stream()))
 
     def wait_next(self):
         """Current stream waits until every rank has published one more step than the last wait_next() saw."""
@@ -181,7 +190,7 @@ class PeerGather:
         if getattr(self, "_base", None):
             torch.cuda.synchronize(self.device)
             if self._fused is not None:
-                self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0, None, None, None, 0)
+                self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0)
                 self._fused = None
             if self.ws > 1:
                 dist.barrier()
@@ -259,6 +268,7 @@ class ShardedBatch:
         if self._flat is not None and st is not None and rw is not None:
             if self.transport == "fused":
                 self._peer.step += 1
+                self._peer.signal_next()
                 self._work = "fused"
                 if not async_gather:
                     self.wait()

@@ -97,7 +97,7 @@ def test_fused_gather_single_rank_matches_plain_step():
         torch.cuda.synchronize()
         sb._peer.check()
         assert torch.equal(gs, st) and torch.equal(gr, rw), k
-    assert int(sb._peer._steps_dev[0]) == 5 and int(sb._peer._steps_dev[1]) == 5
+    assert int(sb._peer._steps_dev[0]) == 5 and int(sb._peer._steps_dev[1]) == 5      # published / awaited
     sb._peer.close()
 
 
