@@ -30,10 +30,17 @@ N, M, NSUB = 32, 32, 10
 L_DOM, DT, NU, TEND = 2 * np.pi, 1e-3, 0.02, 5.0
 POOL = 24                  # independent batches rotated so the working set exceeds L2
 STABLE_SEEDS = (50, 59, 81, 89)
-# algorithmic bytes one launch must move per environment (DESIGN.md "Roofline"):
-#   read  actions M*8 + v,Fn_old 2*(N/2+1)*16 + Ek sums (N/2+1)*4 + counters 28 + forcing 48
-#   write v,Fn_old 2*(N/2+1)*16 + Ek sums + u_prev N*8 + state N*8 + reward 8 + counters 12
-BYTES_PER_ENV_LAUNCH = (M * 8 + 2 * 17 * 16 + 17 * 4 + 28 + 48) + (2 * 17 * 16 + 17 * 4 + N * 8 + N * 8 + 8 + 12)
+# ALGORITHMIC bytes per environment per LAUNCH (Burgers C2, per-step-I/O figure of one state round
+# trip; with NSUB fused sub-steps the state makes that round trip once per launch, so bytes per env-step = 1912 / NSUB):
+#   read  actions M*8 + v,Fn_old 2*(N+2)*8 + forcing coefficients 6*8 + Ek sums (N/2)*8
+#   write v,Fn_old 2*(N+2)*8 + Ek sums (N/2)*8 + state S*8 + reward A*8          = 8*(32+136+6+32+32+1) = 1912 B
+# (the kernel's own layout moves a little less: float32 Ek sums, no u_prev row for state version 0 -> 1844 B)
+BYTES_PER_ENV_LAUNCH = 8 * (M + 4 * (N + 2) + 6 + N + N + 1)
+FLOPS_PER_ENV_STEP = 2600           # algorithmic fp64 flops of one Burgers N=32 solver step
+FP64_PEAK_TFLOPS = 33.2             # measured on this pool's B200 with tools/microbench.cu (profiles/r1_microbench_b200.md)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary_b1.md): the reads
+# are the cold-cache state + actions; the 3.6 MB of results are still dirty in the 126 MB L2 when the replay ends
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 3.957e6
 
 
 def peaks():
@@ -345,10 +352,18 @@ def gpu_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": how, "kernel": "burgers_warp_kernel<double,32>",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": how,
+                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,LEAN>",
                          "bytes_per_launch": B_PER_GPU * BYTES_PER_ENV_LAUNCH,
-                         "note": "launch-latency bound at B=4096 (7.6 MB per launch); 10 fused sub-steps per launch "
-                                 "make the kernel FP64/shuffle bound, see DESIGN.md and profiles/"},
+                         "launch_us": per_launch_s * 1e6,
+                         "note": "algorithmic bytes = 1912 B per env per launch (SURVEY 8d) x 4096 envs; the 10 solver "
+                                 "steps fused into one launch keep the state on chip, so the launch is bound by FP64 + "
+                                 "shuffle issue and their latencies, not by HBM (see roofline_fp64, DESIGN.md 5, profiles/)"},
+            "roofline_fp64": {"bound": "fp64", "achieved": B_PER_GPU * NSUB * FLOPS_PER_ENV_STEP / per_launch_s / 1e12,
+                              "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                              "frac": B_PER_GPU * NSUB * FLOPS_PER_ENV_STEP / per_launch_s / 1e12 / FP64_PEAK_TFLOPS,
+                              "peak_source": "measured (tools/microbench.cu DFMA loop)",
+                              "note": "2.6 kflop per env-step (SURVEY 8d) x 40960 env-steps per launch"},
             "all_envs_alive": alive,
         }
         if world == 1 and not args.no_cpu:

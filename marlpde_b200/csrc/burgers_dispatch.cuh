@@ -34,8 +34,7 @@ int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
     constexpr int wpc = WARPS_PER_CTA;
     const int block = 32 * wpc;
     const int grid = (int)((warps + wpc - 1) / wpc);
-    const int scr = (p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2) + BurgersWarp<T, N, TS, SF, LEAN>::STASH;
-    const size_t smem = (size_t)wpc * TPW * scr * sizeof(T);
+    const size_t smem = (size_t)wpc * TPW * BurgersWarp<T, N, TS, SF, LEAN>::scratch_doubles(p.M) * sizeof(T);
     // programmatic dependent launch: this kernel may become resident (and read its constant tables) while the
     // previous kernel of the stream drains; it reads mutable state only after pdl_wait().  MPDE_PDL=0 disables.
     static const bool pdl = [] { const char* s = std::getenv("MPDE_PDL"); return !(s && s[0] == '0'); }();
@@ -86,8 +85,9 @@ int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
     template int launch_burgers_##N_##_##TS_<double>(const SpectralParams<double>&, cudaStream_t);            \
     template int launch_burgers_##N_##_##TS_<float>(const SpectralParams<float>&, cudaStream_t);
 
-// Team size: the widest team (lowest latency) unless the batch is large enough to keep every
-// SM sub-partition busy with narrower teams (fewer instructions per environment).
+// Team size: the widest team (lowest latency) unless the batch is large enough to give every SM sub-partition
+// ~1.5 warps of the next narrower team (fewer shuffle stages and instructions per environment, more ILP per lane).
+// Measured on B200, fp64 N = 32, B = 4096, 10 sub-steps: 16 lanes 15.2 us, 8 lanes 14.1 us, 4 lanes 26 us.
 // MPDE_TS overrides (tuning).
 inline int pick_team(int64_t B, int N, int ts_max, int ts_min) {
     if (const char* s = std::getenv("MPDE_TS")) {
@@ -95,7 +95,8 @@ inline int pick_team(int64_t B, int N, int ts_max, int ts_min) {
         if (v >= ts_min && v <= ts_max && (v & (v - 1)) == 0) return v;
     }
     int ts = ts_max;
-    while (ts > ts_min && (B * (ts / 2) / 32) >= (int64_t)148 * 4 * MPDE_WARPS_PER_SMSP_TARGET) ts /= 2;
+    // (more than 2 complex points per lane only pays for much larger batches: register pressure)
+    while (ts > ts_min && 2 * (B * (ts / 2) / 32) >= (int64_t)148 * 4 * MPDE_HALF_WARPS_PER_SMSP_TARGET * ((N / 2) / (ts / 2) > 2 ? 4 : 1)) ts /= 2;
     return ts;
 }
 

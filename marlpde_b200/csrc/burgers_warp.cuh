@@ -38,6 +38,14 @@ struct BurgersWarp {
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
     // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row
     static constexpr int STASH = 6 + H;
+    // doubles of shared memory per team: [FFT exchange area | work (dense actions / state gather / MSE) | stash]
+    __host__ __device__ static constexpr int work_doubles(int M) { return M > 2 * N + N / 2 ? M : 2 * N + N / 2; }
+    __host__ __device__ static constexpr int scratch_doubles(int M) {
+        int scr = (2 * R::SMEM_CX + work_doubles(M) + STASH + 1) & ~1;      // 16-byte granularity
+        if (R::SMEM_CX)                                                      // team stride = 64 (mod 128) bytes: see WarpFFT<T,16,4>
+            while ((scr & 15) != 8) scr += 2;
+        return scr;
+    }
 
     // all cross-lane traffic is scoped to the team (f.c.tmask): teams share a warp but never
     // each other's control flow or data
@@ -84,18 +92,19 @@ struct BurgersWarp {
         const int wpc = blockDim.x >> 5;
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
         if (first >= prm.B) return;                                  // whole warp idle 
-        R f;
-        f.init(prm.tw);
-        const int tl = f.c.tl;
         const int team = lane / TS;
+        const int scr = scratch_doubles(prm.M);
+        T* const team_smem = smem + (size_t)(warp * TPW + team) * scr;
+        R f;
+        f.init(prm.tw, reinterpret_cast<Cx<T>*>(team_smem));
+        const int tl = f.c.tl;
         const int64_t e = first + team;
         const bool has = e < prm.B;
         const int64_t ec = has ? e : 0;
         const int flags = SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF);
         const bool q1 = !(flags & F_FORCING);
-        const int scr = max(prm.M, 2 * N + N / 2) + STASH;
-        T* scratch = smem + (size_t)(warp * TPW + team) * scr;
-        T* stash = scratch + (scr - STASH);      // per-team constants parked in shared memory (register relief)
+        T* scratch = team_smem + 2 * R::SMEM_CX;
+        T* stash = scratch + work_doubles(prm.M);      // per-team constants parked in shared memory (register relief)
 
         // ---- constant tables first: they may be read while the previous kernel of the stream still runs ----
         int kk[P];

@@ -31,6 +31,7 @@ template <typename T, int H, int TS_ = (H < 32 ? H : 32), int TWS = 1>
 struct WarpFFT {
     static constexpr int TS = TS_;
     static constexpr int P = H / TS;
+    static constexpr int SMEM_CX = 0;   // complex words of shared memory per team (none: shuffles only)
     static_assert(TS >= 1 && TS <= 32 && (TS & (TS - 1)) == 0 && TS <= H, "team size: power of two, <= 32, <= H");
     static constexpr int LOGH = ilog2(H);
     static constexpr int LOGTS = ilog2(TS);
@@ -54,7 +55,7 @@ struct WarpFFT {
         return (int)(__brev((unsigned)(p * TS + t)) >> (32 - LOGH));
     }
 
-    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw) {
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw, Cx<T>* /*team_smem*/ = nullptr) {
         const int lane = threadIdx.x & 31;
         tl = lane & (TS - 1);
         base = lane & ~(TS - 1);
@@ -173,6 +174,98 @@ struct WarpFFT {
     }
 };
 
+// 16 points on 4 lanes x 4 registers as a 4 x 4 Cooley-Tukey transform: an in-register radix-4 pass, twiddles, a
+// TRANSPOSE through shared memory (4 STS.128 + 4 LDS.128 per lane, bank-conflict free) and a second in-register
+// radix-4 pass.  Against the shuffle butterflies above this moves each value across lanes once instead of
+// log2(TS) times and needs no multiplies in the passes: per lane 44 FP64 + 8 LSU instructions instead of
+// ~90 FP64 + 32 SHFL.  Point j = 4 p + tl lives in register p of lane tl; wavenumber k = tl + 4 d in register d
+// (NATURAL order in and out).  The team's exchange area is SMEM_CX complex words; a team stride of
+// 64 (mod 128) bytes keeps the two teams of a quarter-warp on disjoint banks.
+template <typename T, int TWS>
+struct WarpFFT<T, 16, 4, TWS> {
+    static constexpr int H = 16, TS = 4, P = 4;
+    static constexpr int SMEM_CX = 32;  // two 16-entry slots (fwd2 transforms two sequences at once)
+    int tl, base;
+    unsigned tmask;
+    Cx<T> wl[3];                        // W16^(tl * r), r = 1..3
+    Cx<T>* sm;
+
+    __device__ __forceinline__ static int kidx(int p, int t) { return t + 4 * p; }
+
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw, Cx<T>* team_smem) {
+        const int lane = threadIdx.x & 31;
+        tl = lane & 3;
+        base = lane & ~3;
+        tmask = 0xfu << base;
+        sm = team_smem;
+#pragma unroll
+        for (int r = 1; r < 4; ++r) {           // the table holds W16^m for m < 8; W16^(m+8) = -W16^m  (tl * r <= 9)
+            const int m = tl * r;
+            const Cx<T> w = ldcx(tw + (m & 7) * TWS);
+            wl[r - 1] = m >= 8 ? cx<T>(-w.re, -w.im) : w;
+        }
+    }
+
+    // 4-point DFT of the registers; INV = conjugate twiddles (W4 = +i)
+    template <bool INV>
+    __device__ __forceinline__ static void dft4(Cx<T> (&x)[4]) {
+        const Cx<T> a0 = x[0] + x[2], a1 = x[0] - x[2], a2 = x[1] + x[3], a3 = x[1] - x[3];
+        x[0] = a0 + a2;
+        x[2] = a0 - a2;
+        // forward: y1 = a1 - i a3, y3 = a1 + i a3
+        const Cx<T> m = cx<T>(a1.re + a3.im, a1.im - a3.re), q = cx<T>(a1.re - a3.im, a1.im + a3.re);
+        x[1] = INV ? q : m;
+        x[3] = INV ? m : q;
+    }
+    // element (lane a, register b) -> (lane b, register a); entry of (destination lane b, register a) is
+    // 4 b + ((a + b) & 3): writes of one register fill one 64-byte block, reads of one register hit 4 distinct
+    // bank groups
+    __device__ __forceinline__ void put(const Cx<T> (&z)[4], int slot) const {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) stcx(sm + 16 * slot + 4 * b + ((tl + b) & 3), z[b]);
+    }
+    __device__ __forceinline__ void get(Cx<T> (&z)[4], int slot) const {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) z[a] = ldcx(sm + 16 * slot + 4 * tl + ((a + tl) & 3));
+    }
+    template <bool INV>
+    __device__ __forceinline__ void twiddle(Cx<T> (&z)[4]) const {
+#pragma unroll
+        for (int r = 1; r < 4; ++r) z[r] = INV ? cmulc(z[r], wl[r - 1]) : cmul(z[r], wl[r - 1]);
+    }
+    template <bool INV>
+    __device__ __forceinline__ void run(Cx<T> (&z)[4]) const {
+        dft4<INV>(z);
+        twiddle<INV>(z);
+        __syncwarp(tmask);
+        put(z, 0);
+        __syncwarp(tmask);
+        get(z, 0);
+        dft4<INV>(z);
+    }
+    __device__ __forceinline__ void fwd(Cx<T> (&z)[4]) const { run<false>(z); }
+    __device__ __forceinline__ void inv(Cx<T> (&z)[4]) const { run<true>(z); }
+    __device__ __forceinline__ void fwd2(Cx<T> (&za)[4], Cx<T> (&zb)[4]) const {
+        dft4<false>(za);
+        dft4<false>(zb);
+        twiddle<false>(za);
+        twiddle<false>(zb);
+        __syncwarp(tmask);
+        put(za, 0);
+        put(zb, 1);
+        __syncwarp(tmask);
+        get(za, 0);
+        get(zb, 1);
+        dft4<false>(za);
+        dft4<false>(zb);
+    }
+    // value held for wavenumber -k (mod 16): k = tl + 4 p -> lane (4 - tl) & 3, register 3 - p (tl > 0) or (4 - p) & 3
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[4], int p) const {
+        const Cx<T> far = shfl(z[3 - p], base + ((4 - tl) & 3), tmask);
+        return tl == 0 ? z[(4 - p) & 3] : far;
+    }
+};
+
 template <typename T, int N, int TS_ = (N / 2 < 32 ? N / 2 : 32)>
 struct RealFFT {
     static constexpr int H = N / 2;
@@ -184,8 +277,9 @@ struct RealFFT {
     Cx<T> wk[P];     // exp(-2 pi i k / N) for the wavenumber k of register p
     bool dc;         // this lane's register 0 holds k = 0 (and owns the Nyquist value)
 
-    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw /* [N/2]: exp(-2 pi i j / N) */) {
-        c.init(tw);
+    static constexpr int SMEM_CX = C::SMEM_CX;       // complex words of shared memory this transform needs per team
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw /* [N/2]: exp(-2 pi i j / N) */, Cx<T>* team_smem = nullptr) {
+        c.init(tw, team_smem);
 #pragma unroll
         for (int p = 0; p < P; ++p) wk[p] = ldcx(tw + C::kidx(p, c.tl));
         dc = c.tl == 0;
