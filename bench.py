@@ -156,14 +156,14 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, transport=None):
     return {"workload": f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
                         f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
                         f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of the batch",
             "envs_per_gpu": B_PER_GPU, "N": N, "M": M, "n_intermediate": NSUB, "global_envs": B_PER_GPU * n_gpus,
             "l2": f"rotating pool of {POOL} independent batches per GPU (state working set > 126 MB L2)",
-            "parallelism": (f"env-sharded x{n_gpus}, state+reward gathered to every rank per RL step by peer stores fused into "
-                            "the step kernel (NVLink, no NCCL call)") if n_gpus > 1 else "single GPU"}
+            "parallelism": (f"env-sharded x{n_gpus}, state+reward gathered to every rank per RL step by {transport or 'peer'} "
+                            "stores fused into the step kernel (NVLink / NVSwitch, no NCCL call)") if n_gpus > 1 else "single GPU"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -343,7 +343,9 @@ def gpu_arm(args):
         line = {
             "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic",
+            "config": workload_config(world, ("multicast (multimem.st, %s memory)" if gathers[0].multicast else "unicast peer (%s memory)")
+                                      % gathers[0].backend if gathers else None),
             "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": Ke, "batches_in_flight": depth,

@@ -189,12 +189,16 @@ const char* mpde_peer_last_error(void);
  * by the library on the host) writes every buffer -- the local state_out / reward_out included -- at an offset of
  * (s & 1) * parity_stride ELEMENTS, so a fast rank's next step never lands in rows a slower rank's learner is still
  * reading (a CUDA graph that replays steps of `env` must therefore hold an even number of them).
- * n_data = 0 and parity_stride = 0 unbinds.
+ * mc_state / mc_reward (both or neither): this rank's slab addressed through an NVSwitch MULTICAST mapping of the gather
+ * buffers (cuMulticast* / torch symmetric memory): one multimem.st per row then reaches every rank, this one included,
+ * replacing the local store and the per-peer loop (pass n_data = 0).
+ * n_data = 0, parity_stride = 0 and no multicast pointers unbinds.
  * Publishing is stream-ordered behind the step: mpde_peer_signal_next bumps *step_dev (int64, device) and stores it to
  * the n addresses flag_ptrs[j] = &flag_array_of_rank_j[my rank] (this rank included); mpde_peer_wait_next makes the
  * stream wait until every slot of this rank's flag array has reached ++(*expect_dev).  All counters live on the device,
  * so step + signal + wait replay from a CUDA graph; neither needs to sit on the step kernels' own stream. */
-int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride);
+int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride,
+                         void* mc_state, void* mc_reward);
 int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream);
 int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
 /* signal_next + wait_next as ONE kernel launch */

@@ -541,6 +541,10 @@ struct BurgersWarp {
                 const Cx<T> ii = cx<T>(inf, inf);
                 // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
                 auto put = [&](int64_t idx, Cx<T> val) {
+                    if (prm.peer.mc_state) {      // one multicast store reaches every rank's buffer (this one included)
+                        st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + idx, val);
+                        return;
+                    }
                     stcx(reinterpret_cast<Cx<T>*>(state_out + off) + idx, val);
                     for (int q = 0; q < prm.peer.n_data; ++q)
                         stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + idx, val);
@@ -608,8 +612,12 @@ struct BurgersWarp {
                         val = f0[2 * N + (r - nf * seg)];
                     }
                     const T out = live ? val : inf;                        // Burger.py:633-643
-                    state_out[e * S + o] = out;
-                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.state[q])[poff + e * S + o] = out;
+                    if (prm.peer.mc_state) {
+                        st_multicast(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o, out);
+                    } else {
+                        state_out[e * S + o] = out;
+                        for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.state[q])[poff + e * S + o] = out;
+                    }
                 }
             }
             __syncwarp(f.c.tmask);
@@ -631,8 +639,12 @@ struct BurgersWarp {
             const T r = live ? stash[4] - part : -inf;
             if (has) {
                 for (int a = tl; a < A; a += TS) {
-                    reward_out[e * A + a] = r;
-                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
+                    if (prm.peer.mc_reward) {
+                        st_multicast(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a, r);
+                    } else {
+                        reward_out[e * A + a] = r;
+                        for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
+                    }
                 }
                 if (f.dc && live) prm.kprev[e] = part;
             }
@@ -658,8 +670,12 @@ struct BurgersWarp {
                     T sum = T(0);
                     for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
                     const T r = live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
-                    reward_out[e * A + a] = r;
-                    for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
+                    if (prm.peer.mc_reward) {
+                        st_multicast(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a, r);
+                    } else {
+                        reward_out[e * A + a] = r;
+                        for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
+                    }
                 }
             }
         }

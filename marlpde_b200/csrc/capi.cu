@@ -49,7 +49,8 @@ struct mpde_env {
     virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
-    virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride) = 0;
+    virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
+                                void* mc_reward) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -267,11 +268,12 @@ struct Env : mpde_env {
         return 0;
     }
 
-    int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride) override {
+    int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
+                        void* mc_reward) override {
         peer_bound = false;
         peer_steps = 0;
         prm.peer = PeerSink{};
-        if (n_data == 0 && parity_stride == 0) return 0;
+        if (n_data == 0 && parity_stride == 0 && !mc_state) return 0;
         if (cfg.equation != MPDE_BURGERS || cfg.N > 256)
             return fail("set_peer_output: the fused gather exists for the warp-resident Burgers kernels (N <= 256) only; "
                         "use mpde_peer_put for the other solvers");
@@ -285,6 +287,9 @@ struct Env : mpde_env {
             ps.reward[i] = reward[i];
         }
         ps.parity_stride = parity_stride;
+        if ((mc_state == nullptr) != (mc_reward == nullptr)) return fail("set_peer_output: multicast needs both pointers");
+        ps.mc_state = mc_state;
+        ps.mc_reward = mc_reward;
         prm.peer = ps;
         peer_bound = true;
         return 0;
@@ -600,9 +605,10 @@ int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out,
 int mpde_step_host(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step_host(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
-int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride) {
+int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride,
+                         void* mc_state, void* mc_reward) {
     if (env) ++env->epoch;
-    return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, parity_stride) : fail("null argument");
+    return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, parity_stride, mc_state, mc_reward) : fail("null argument");
 }
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");

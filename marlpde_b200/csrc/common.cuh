@@ -58,6 +58,20 @@ template <typename T> __device__ __forceinline__ bool blown(Cx<T> v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Stores to an NVSwitch multicast address (multimem.st, sm_90+): the switch replicates the store into the
+// buffer of every GPU bound to the multicast object.  Plain bit moves (no reduction).
+__device__ __forceinline__ void st_multicast(double* p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_multicast(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_multicast(Cx<double>* p, Cx<double> v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__int_as_float(__double2loint(v.re))),
+                 "f"(__int_as_float(__double2hiint(v.re))), "f"(__int_as_float(__double2loint(v.im))),
+                 "f"(__int_as_float(__double2hiint(v.im)))
+                 : "memory");
+}
+__device__ __forceinline__ void st_multicast(Cx<float>* p, Cx<float> v) {
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.re), "f"(v.im) : "memory");
+}
+
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
 }  // namespace mpde

@@ -33,6 +33,11 @@ struct PeerSink {
                                     // rank's learner is still reading
     void* state[MAX_PEERS] = {};    // peer p: where this rank's [B,S] state slab lives in p's gather buffer
     void* reward[MAX_PEERS] = {};   // peer p: where this rank's [B,A] reward slab lives
+    // NVSwitch multicast (NVLS) alternative: ONE multimem.st per row lands in every rank's buffer (this rank's
+    // included), so a rank sends its slab once instead of once per peer.  Set -> replaces the local store and
+    // the per-peer loop.
+    void* mc_state = nullptr;
+    void* mc_reward = nullptr;
 };
 
 template <typename T>

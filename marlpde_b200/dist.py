@@ -76,7 +76,7 @@ class PeerGather:
     consumer side and ``current()`` the [world_size, chunk_elems] copy the last step wrote (double-buffered).
     """
 
-    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24, copies=1):
+    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24, copies=1, backend="auto"):
         import ctypes as C
         from . import _lib as LB
         self._C, self._lib = C, LB.lib()
@@ -89,24 +89,56 @@ class PeerGather:
         self._copy_bytes = self.ws * self.chunk_bytes
         gbytes = self.copies * self._copy_bytes
         total = gbytes + 16 * ((self.ws * 8 + 15) // 16)
-        base = C.c_void_p()
-        self._check(self._lib.mpde_peer_alloc(total, C.byref(base)))
-        self._base = base.value
-        handle = (C.c_ubyte * 64)()
-        self._check(self._lib.mpde_peer_export(self._base, handle))
-        handles = [None] * self.ws
-        if self.ws > 1:
-            dist.all_gather_object(handles, bytes(handle))
+        # Backing memory: "symm" = torch symmetric memory (plumbing: cuMem + fabric handles), which also maps the
+        # buffers of all ranks behind ONE NVSwitch multicast address when the box supports NVLS; "ipc" = cudaMalloc +
+        # CUDA IPC handles (unicast peer pointers only).  "auto" tries symm and falls back to ipc on every rank alike.
+        import os
+        backend = os.environ.get("MPDE_PEER_BACKEND", backend)          # auto | symm | ipc (tests / tuning)
+        self.backend, self.multicast_base, self._symm, self.multicast = "ipc", 0, None, False
         self._peer_bases, self._opened = [], []
-        for r in range(self.ws):
-            if r == self.rank:
-                self._peer_bases.append(self._base)
-            else:
-                p = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-                self._check(self._lib.mpde_peer_open(buf, C.byref(p)))
-                self._peer_bases.append(p.value)
-                self._opened.append(p.value)
+        if backend in ("auto", "symm") and self.ws > 1:
+            ok = 0
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty(total, dtype=torch.uint8, device=self.device)
+                hdl = symm.rendezvous(t, dist.group.WORLD)
+                ok = 1
+            except Exception as e:           # no cuMem/fabric support in this container, old torch, ...
+                if backend == "symm":
+                    raise
+                self._symm_error = repr(e)
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                t.zero_()
+                self._symm = (t, hdl)
+                self.backend = "symm"
+                self._base = t.data_ptr()
+                self._peer_bases = [int(p) for p in hdl.buffer_ptrs]
+                assert self._peer_bases[self.rank] == self._base
+                self.multicast_base = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                mc = torch.tensor([1 if self.multicast_base else 0], device=self.device)
+                dist.all_reduce(mc, op=dist.ReduceOp.MIN)
+                if int(mc.item()) == 0:
+                    self.multicast_base = 0
+        if self.backend == "ipc":
+            base = C.c_void_p()
+            self._check(self._lib.mpde_peer_alloc(total, C.byref(base)))
+            self._base = base.value
+            handle = (C.c_ubyte * 64)()
+            self._check(self._lib.mpde_peer_export(self._base, handle))
+            handles = [None] * self.ws
+            if self.ws > 1:
+                dist.all_gather_object(handles, bytes(handle))
+            for r in range(self.ws):
+                if r == self.rank:
+                    self._peer_bases.append(self._base)
+                else:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    self._check(self._lib.mpde_peer_open(buf, C.byref(p)))
+                    self._peer_bases.append(p.value)
+                    self._opened.append(p.value)
         arr = C.c_void_p * self.ws
         self._dst = arr(*[b for b in self._peer_bases])
         self._flags = arr(*[b + gbytes for b in self._peer_bases])
@@ -141,7 +173,7 @@ class PeerGather:
         self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err.data_ptr(), self.max_spins,
                                              self._stream()))
 
-    def fuse(self, env, n_local, S, A):
+    def fuse(self, env, n_local, S, A, use_multicast=True):
         """Let ``env``'s step kernel write its [n_local,S] state and [n_local,A] reward straight into this rank's slab
         of every rank's buffer and publish the step itself (no put kernel, no NCCL)."""
         C = self._C
@@ -156,7 +188,15 @@ class PeerGather:
         arr_f = C.c_void_p * self.ws
         self._flag_slots = arr_f(*[self._peer_bases[r] + self.copies * self._copy_bytes + 8 * self.rank for r in range(self.ws)])
         stride = self._copy_bytes // self._item if self.copies == 2 else 0
-        rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, stride)
+        mc_state = mc_reward = None
+        import os
+        if self.multicast_base and use_multicast and os.environ.get("MPDE_MULTICAST", "1") != "0":
+            # one multimem.st per row reaches every rank (this one included): no per-peer stores at all
+            mc_state = self.multicast_base + slab
+            mc_reward = mc_state + n_local * S * self._item
+            others = []
+        self.multicast = mc_state is not None
+        rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, stride, mc_state, mc_reward)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         self._fused = env
@@ -190,13 +230,15 @@ class PeerGather:
         if getattr(self, "_base", None):
             torch.cuda.synchronize(self.device)
             if self._fused is not None:
-                self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0)
+                self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0, None, None)
                 self._fused = None
             if self.ws > 1:
                 dist.barrier()
             for p in self._opened:
                 self._lib.mpde_peer_close(p)
-            self._lib.mpde_peer_free(self._base)
+            if self.backend == "ipc":
+                self._lib.mpde_peer_free(self._base)
+            self._symm = None
             self._base = None
 
 

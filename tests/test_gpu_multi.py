@@ -27,6 +27,9 @@ def _acts():
 
 def _worker(rank, ws, port, q, transport="nccl"):
     import torch.distributed as dist
+    if transport == "fused-ipc":            # force the CUDA-IPC / unicast path (the default tries NVSwitch multicast)
+        os.environ["MPDE_PEER_BACKEND"] = "ipc"
+        transport = "fused"
     from marlpde_b200 import dist as mdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -39,6 +42,7 @@ def _worker(rank, ws, port, q, transport="nccl"):
         torch.cuda.synchronize()
         if transport in ("p2p", "fused"):
             sb._peer.check()
+            print(f"[rank {rank}] transport={transport} backend={sb._peer.backend} multicast={sb._peer.multicast}", flush=True)
         q.put((rank, gs.cpu().numpy(), gr.cpu().numpy()))
         if transport in ("p2p", "fused"):
             sb._peer.close()
@@ -47,10 +51,10 @@ def _worker(rank, ws, port, q, transport="nccl"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused", "fused-ipc"])
 def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     import torch.multiprocessing as mp
-    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100}[transport]
+    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100, "fused-ipc": 150}[transport]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q, transport)) for r in range(ws)]
