@@ -85,19 +85,19 @@ int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
     template int launch_burgers_##N_##_##TS_<double>(const SpectralParams<double>&, cudaStream_t);            \
     template int launch_burgers_##N_##_##TS_<float>(const SpectralParams<float>&, cudaStream_t);
 
-// Team size: the widest team (lowest latency) unless the batch is large enough to give every SM sub-partition
-// ~1.5 warps of the next narrower team (fewer shuffle stages and instructions per environment, more ILP per lane).
-// Measured on B200, fp64 N = 32, B = 4096, 10 sub-steps: 16 lanes 15.2 us, 8 lanes 14.1 us, 4 lanes 26 us.
-// MPDE_TS overrides (tuning).
-inline int pick_team(int64_t B, int N, int ts_max, int ts_min) {
+// Team size = lanes per environment.  It is a function of N ONLY (two complex points per lane: N = 32 -> 8 lanes,
+// N = 64 -> 16 lanes), never of the batch size: the variants factor the FFT differently, so their results differ in
+// the last bits, and environment e must give the same bits whether it runs alone or inside a batch of 65536.
+// Measured on B200, fp64 N = 32, B = 4096, 10 sub-steps: 16 lanes 15.2 us, 8 lanes 13.9 us, 4 lanes 14.7 us per launch
+// (the 4-lane shared-memory-transpose variant has the lowest per-step slope and wins from B ~ 8192 per GPU).
+// MPDE_TS selects another variant for the whole process (tuning / tests; not bitwise compatible with the default).
+inline int pick_team(int64_t /*B*/, int N, int ts_max, int ts_min) {
     if (const char* s = std::getenv("MPDE_TS")) {
         const int v = std::atoi(s);
         if (v >= ts_min && v <= ts_max && (v & (v - 1)) == 0) return v;
     }
-    int ts = ts_max;
-    // (more than 2 complex points per lane only pays for much larger batches: register pressure)
-    while (ts > ts_min && 2 * (B * (ts / 2) / 32) >= (int64_t)148 * 4 * MPDE_HALF_WARPS_PER_SMSP_TARGET * ((N / 2) / (ts / 2) > 2 ? 4 : 1)) ts /= 2;
-    return ts;
+    const int ts = N / 4;           // P = (N/2) / ts = 2 complex points per lane
+    return ts > ts_max ? ts_max : (ts < ts_min ? ts_min : ts);
 }
 
 }  // namespace mpde

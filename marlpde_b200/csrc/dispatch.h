@@ -6,9 +6,7 @@
 #include "params.h"
 #include "pack.cuh"
 
-#ifndef MPDE_HALF_WARPS_PER_SMSP_TARGET
-#define MPDE_HALF_WARPS_PER_SMSP_TARGET 3      // pick_team: 1.5 warps per SM sub-partition
-#endif
+
 
 namespace mpde {
 
