@@ -74,10 +74,11 @@ struct BurgersWarp {
                     right[p] = shfl(x[p].re, lr, f.c.tmask);
                     left[p] = shfl(x[p].im, ll, f.c.tmask);
                 } else {
-                    const T a = shfl(x[p].re, lr, f.c.tmask), b = shfl(x[(p + 1) % P].re, lr, f.c.tmask);
-                    right[p] = (tl == TS - 1) ? b : a;
-                    const T c = shfl(x[p].im, ll, f.c.tmask), d = shfl(x[(p + P - 1) % P].im, ll, f.c.tmask);
-                    left[p] = (tl == 0) ? d : c;
+                    // the SENDER picks the register: lane 0 holds the point right of lane TS-1's register p-1 ...
+                    const T sr = (tl == 0) ? x[(p + 1) % P].re : x[p].re;          // wanted by my left neighbour
+                    const T sl = (tl == TS - 1) ? x[(p + P - 1) % P].im : x[p].im;  // wanted by my right neighbour
+                    right[p] = shfl(sr, lr, f.c.tmask);
+                    left[p] = shfl(sl, ll, f.c.tmask);
                 }
             }
         }
@@ -160,6 +161,18 @@ struct BurgersWarp {
                 }
         }
         const T v0im = v[0].im;                 // meaningful on the dc lane only
+        // reference spectrum row of the step this call ends at + kPrevRelErr: their addresses depend on iout, so the
+        // loads go out as early as possible; the values are parked in shared memory at the end of the prologue
+        const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
+        const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
+        T ek_pre[P], kprev_pre = T(0);
+        if (spec_reward) {
+            const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
+            const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
+#pragma unroll
+            for (int p = 0; p < P; ++p) ek_pre[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+            kprev_pre = prm.kprev[ec];
+        }
 
         // ---- per-register constants -------------------------------------------------------
         const T dt = prm.dt;
@@ -271,16 +284,10 @@ struct BurgersWarp {
         bool bad = false;
 
         // =============================== sub-steps ==============================================
-        const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
-        // reference spectrum row of the step this call ends at + kPrevRelErr: fetched now (off the critical
-        // path of the epilogue), parked in shared memory until the reward is evaluated
-        const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
         if (spec_reward) {
-            const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
-            const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
 #pragma unroll
-            for (int p = 0; p < P; ++p) stash[5 + kk[p]] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
-            if (f.dc) stash[4] = prm.kprev[ec];
+            for (int p = 0; p < P; ++p) stash[5 + kk[p]] = ek_pre[p];
+            if (f.dc) stash[4] = kprev_pre;
         }
         __syncwarp(f.c.tmask);
         const bool hist = !LEAN && prm.hist_rows > 0;
