@@ -138,6 +138,20 @@ int mpde_set_history(mpde_env* env, void* uu_dev, void* vv_dev, double* ektt_dev
 int mpde_reset_u(mpde_env* env, const void* u0_dev, const uint8_t* mask_dev, void* stream);
 int mpde_reset_v(mpde_env* env, const void* v0_dev, const uint8_t* mask_dev, void* stream);
 
+/* Episode reset without a host loop.
+ * mpde_reset_handoff: the DNS -> LES spectral hand-off of burger_environment.py:109-112 / ks_environment.py:52-54 for
+ *   every (masked) environment e:  v0_e = concat(w[:(N+1)//2], w[-(N-1)//2:]) * N / nsrc_points,
+ *   w = vsrc[src_map[e]] * exp(1j * 2 pi * offset[e] * ksrc), followed by IC(v0 = v0_e).
+ *   vsrc_dev: DEVICE complex128 [nsrc, nsrc_points] (dns.v0), ksrc_dev: DEVICE double [nsrc_points] (dns.k),
+ *   src_map_dev int32 [B] or NULL (all use source 0), offset_dev double [B] or NULL (no shift).
+ * mpde_reset_turbulence: IC(case='turbulence') (Burger.py:227-260) for every (masked) environment from its own seed and
+ *   offset: seed_dev int64 [B], offset_dev double [B] or NULL, x_dev double [N] (Burger.x), amp_dev double [N] with
+ *   amp[k] = sqrt(2 E_k), E_k = 5^(-5/3) for k <= 5 else k^(-5/3). */
+int mpde_reset_handoff(mpde_env* env, const void* vsrc_dev, int64_t nsrc, int32_t nsrc_points, const double* ksrc_dev,
+                       const int32_t* src_map_dev, const double* offset_dev, const uint8_t* mask_dev, void* stream);
+int mpde_reset_turbulence(mpde_env* env, const int64_t* seed_dev, const double* offset_dev, const double* x_dev,
+                          const double* amp_dev, const uint8_t* mask_dev, void* stream);
+
 /* step(actions) x nsub + getState + reward (Burger.py:333-499, 604-675; KS.py:230-274, 369-383;
  * Diffusion.py:164-216; Advection.py:154-213; burger_environment.py:148-176).
  *   actions_dev : [B, M] real or NULL (step() without actions)

@@ -147,9 +147,28 @@ class Burger(SpectralEnv):
         return self._squeeze(self._get(LB.FIELD_FN_OLD, (self.nenvs, self.N), self.cdtype))
 
     # ------------------------------------------------------------------ set-up
-    def IC(self, u0=None, v0=None, case='zero', mask=None):
-        """Burger.py:205-320.  u0 / v0: [N] (shared) or [B, N]; ``mask`` resets a subset."""
+    def IC(self, u0=None, v0=None, case='zero', mask=None, on_device=None):
+        """Burger.py:205-320.  u0 / v0: [N] (shared) or [B, N]; ``mask`` resets a subset.
+        case='turbulence' with many distinct (seed, offset) pairs is generated on the device (one CTA per
+        environment, mpde_reset_turbulence) instead of in a host loop; ``on_device`` forces either path."""
         B, N = self.nenvs, self.N
+        if v0 is None and u0 is None and case == 'turbulence':
+            if on_device is None:
+                on_device = len({(int(a), float(b)) for a, b in zip(self.seeds, self._offset)}) > 16
+            if on_device:
+                k = np.arange(N, dtype=np.float64)
+                with np.errstate(divide='ignore'):
+                    Ek = np.where(k <= 5, 5. ** (-5 / 3), k ** (-5 / 3))            # Burger.py:242
+                amp = np.sqrt(2 * Ek)
+                sd = self._dev(self.seeds, torch.int64, (B,))
+                off = self._dev(self._offset, torch.float64, (B,))
+                xd = self._dev(self.x, torch.float64, (N,))
+                ad = self._dev(amp, torch.float64, (N,))
+                m, mp = self._mask_ptr(mask)
+                L_check(self._lib.mpde_reset_turbulence(self._h, self._ptr(sd), self._ptr(off), self._ptr(xd), self._ptr(ad), mp,
+                                                        self._stream()))
+                self._after_reset()
+                return
         if v0 is None:
             if u0 is None:
                 u0 = self._case_field(case)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mpde_reset_u": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mpde_reset_v": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mpde_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "mpde_reset_handoff": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mpde_reset_turbulence": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mpde_step_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mpde_get": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mpde_set": (C.c_int, [_vp, _i32, _vp, _vp]),

@@ -24,6 +24,35 @@ class SpectralEnv(BatchedEnv):
         return self._squeeze(self._get(LB.FIELD_V, (self.nenvs, self.N), self.cdtype))
 
 
+    # ------------------------------------------------------------------ device-side episode reset
+    def IC_handoff(self, src_v0, src_k, src_map=None, offsets=None, mask=None):
+        """DNS -> LES spectral hand-off for the whole batch in one launch (burger_environment.py:109-112,
+        ks_environment.py:52-54):  v0_e = concat(w[:(N+1)//2], w[-(N-1)//2:]) * N / N_src with
+        w = src_v0[src_map[e]] * exp(1j * 2 pi * offsets[e] * src_k), then IC(v0=v0_e).
+        src_v0: [N_src] or [n_src, N_src] complex (dns.v0 of one or several DNS runs), src_k: [N_src] (dns.k)."""
+        B = self.nenvs
+        v = torch.as_tensor(src_v0) if not isinstance(src_v0, torch.Tensor) else src_v0
+        v = v.to(device=self.device, dtype=torch.complex128).reshape(-1, v.shape[-1]).contiguous()
+        k = torch.as_tensor(np.asarray(src_k, dtype=np.float64), device=self.device).contiguous()
+        assert k.numel() == v.shape[1]
+        mp_t = None if src_map is None else self._dev(np.asarray(src_map), torch.int32, (B,))
+        off_t = None if offsets is None else self._dev(np.broadcast_to(np.asarray(offsets, dtype=np.float64), (B,)).copy(),
+                                                       torch.float64, (B,))
+        m, mp = self._mask_ptr(mask)
+        L_check(self._lib.mpde_reset_handoff(self._h, self._ptr(torch.view_as_real(v)), v.shape[0], v.shape[1], self._ptr(k),
+                                             self._ptr(mp_t), self._ptr(off_t), mp, self._stream()))
+        self._after_reset()
+
+    def _after_reset(self):
+        self.t = 0.
+        self.stepnum = 0
+        self.ioutnum = 0
+        self._state_at = self._reward_at = -1
+        if hasattr(self, "_uu_valid_at"):
+            self._uu_valid_at = -1
+        self.u0 = self.u
+        self.v0 = self.v
+
     # ------------------------------------------------------------------ history
     def _setup_history(self, history):
         B, rows, N = self.nenvs, self.nout + 1, self.N

@@ -150,6 +150,10 @@ class BurgerEnvBatch:
                 self.sgs.randfac2 = np.stack([dns_default[i].randfac2[:, :stepper] for i in self.dmap])
         self.sgs.setup_basis(numActions, basis)
         if spectralReward:
+            # all DNS initial spectra on the device once: reset() is ONE hand-off launch for the whole batch
+            self._dns_v0 = torch.stack([torch.as_tensor(d.v0).to(device=d0.device, dtype=torch.complex128).reshape(-1)
+                                        for d in dns_default])
+            self._dns_k = np.asarray(d0.k, dtype=np.float64)
             ref = torch.cat([d._ektt[:, :, :gridSize // 2] for d in dns_default], dim=0)
             self.sgs.set_spectrum_reference(ref, env_map=self.dmap if ndns > 1 else None)
         else:
@@ -167,15 +171,16 @@ class BurgerEnvBatch:
             self._truth = np.stack(tabs)
             self._tmap = inv.astype(np.int32)
             self.sgs.set_truth_table(self._truth, env_map=self._tmap if len(uniq) > 1 else None)
+            self._u0_dev = torch.as_tensor(self._truth[self._tmap, 0], device=d0.device)
 
     def reset(self):
         B, g = self.B, self.gridSize
         off = np.broadcast_to(np.asarray(self.sgs.offset, dtype=np.float64), (B,))
-        if self.spectral:
-            v0 = np.stack([_truncated_v0(self.dns[self.dmap[e]], off[e], g) for e in range(B)])
-            self.sgs.IC(v0=v0)
+        if self.spectral:          # burger_environment.py:109-112 for every environment, on the device
+            self.sgs.IC_handoff(self._dns_v0, self._dns_k, src_map=self.dmap if len(self.dns) > 1 else None,
+                                offsets=off if np.any(off != 0.) else None)
         else:
-            self.sgs.IC(u0=self._truth[self._tmap, 0])
+            self.sgs.IC(u0=self._u0_dev)
         self.step_count = 0
         return self.sgs.getState(as_tensor=True)
 

@@ -47,6 +47,10 @@ struct mpde_env {
     virtual int set_truth(const void* truth, int64_t ntruth, int64_t rows, const int32_t* map) = 0;
     virtual int set_history(void* uu, void* vv, double* ektt, int64_t rows) = 0;
     virtual int reset(const void* src, bool spectral, const uint8_t* mask, cudaStream_t st) = 0;
+    virtual int reset_handoff(const void* vsrc, int64_t nsrc, int nsrc_points, const double* ksrc, const int32_t* src_map,
+                              const double* offset, const uint8_t* mask, cudaStream_t st) = 0;
+    virtual int reset_turbulence(const int64_t* seed, const double* offset, const double* x, const double* amp,
+                                 const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
@@ -311,6 +315,36 @@ struct Env : mpde_env {
         if (rc < 0) return fail("reset: unsupported N for this equation (power of two, 8..2048)");
         CU(cudaGetLastError());
         return 0;
+    }
+
+    // staging field of the device-side IC generators: [B,N] complex (hand-off) or real (turbulence)
+    Cx<T>* ic_stage = nullptr;
+    int ensure_ic_stage() {
+        if (!ic_stage && dalloc(&ic_stage, (size_t)cfg.nenvs * cfg.N)) return -1;
+        return 0;
+    }
+    int reset_handoff(const void* vsrc, int64_t nsrc, int nsrc_points, const double* ksrc, const int32_t* src_map,
+                      const double* offset, const uint8_t* mask, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (!spectral()) return fail("reset_handoff: spectral solvers only");
+        if (!vsrc || !ksrc || nsrc < 1) return fail("reset_handoff: null source");
+        if (nsrc_points < cfg.N) return fail("reset_handoff: the source grid must be at least as fine as the environment grid");
+        if (ensure_ic_stage()) return -1;
+        launches += launch_handoff<T>(vsrc, nsrc_points, ksrc, src_map, offset, mask, ic_stage, cfg.nenvs, cfg.N, st);
+        CU(cudaGetLastError());
+        return reset(ic_stage, true, mask, st);
+    }
+    int reset_turbulence(const int64_t* seed, const double* offset, const double* x, const double* amp, const uint8_t* mask,
+                         cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (!seed || !x || !amp) return fail("reset_turbulence: null argument");
+        if (ensure_ic_stage()) return -1;
+        const int rc = launch_turbulence<T>(reinterpret_cast<const long long*>(seed), offset, x, amp, mask, ic_stage, cfg.nenvs, cfg.N,
+                                            cfg.L, st);
+        if (rc < 0) return fail("reset_turbulence: N <= 2048");
+        launches += rc;
+        CU(cudaGetLastError());
+        return reset(ic_stage, false, mask, st);
     }
 
     int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
@@ -598,6 +632,16 @@ int mpde_reset_u(mpde_env* env, const void* u0, const uint8_t* mask, void* strea
 }
 int mpde_reset_v(mpde_env* env, const void* v0, const uint8_t* mask, void* stream) {
     return env ? env->reset(v0, true, mask, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_reset_handoff(mpde_env* env, const void* vsrc_dev, int64_t nsrc, int32_t nsrc_points, const double* ksrc_dev,
+                       const int32_t* src_map_dev, const double* offset_dev, const uint8_t* mask_dev, void* stream) {
+    return env ? env->reset_handoff(vsrc_dev, nsrc, nsrc_points, ksrc_dev, src_map_dev, offset_dev, mask_dev, static_cast<cudaStream_t>(stream))
+               : fail("null argument");
+}
+int mpde_reset_turbulence(mpde_env* env, const int64_t* seed_dev, const double* offset_dev, const double* x_dev, const double* amp_dev,
+                          const uint8_t* mask_dev, void* stream) {
+    return env ? env->reset_turbulence(seed_dev, offset_dev, x_dev, amp_dev, mask_dev, static_cast<cudaStream_t>(stream))
+               : fail("null argument");
 }
 int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");

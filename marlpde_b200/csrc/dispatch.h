@@ -22,6 +22,12 @@ template <typename T>
 int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
                             void* dst, cudaStream_t st);
 template <typename T> int launch_ks(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T>
+int launch_handoff(const void* vsrc, int nsrc_points, const double* ksrc, const int* src_map, const double* offset,
+                   const uint8_t* mask, void* out, int64_t B, int N, cudaStream_t st);
+template <typename T>
+int launch_turbulence(const long long* seed, const double* offset, const double* x, const double* amp, const uint8_t* mask,
+                      void* out, int64_t B, int N, double L, cudaStream_t st);
 template <typename T> int launch_ks_cta(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_fd(const SpectralParams<T>& p, int equation, bool implicit, cudaStream_t st);
 template <typename T> int launch_fd_reset(const SpectralParams<T>& p, const void* src, const uint8_t* mask, cudaStream_t st);
