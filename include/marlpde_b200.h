@@ -74,7 +74,9 @@ typedef struct mpde_config {
     int32_t stepper;      /* s: forcing column period (Burger.py:416)                              */
     int32_t flags;        /* MPDE_DFORCE | MPDE_FORCING | ...                                      */
     int32_t reward_mode;  /* enum mpde_reward                                                      */
-    int32_t reserved;
+    int32_t team_lanes;   /* 0 = default (N/4 lanes per environment); 4 / 8 / 16 / 32 selects another team size of the
+                           * warp-resident Burgers kernels (N = 32: 4 wins from ~8192 environments per GPU).  Variants
+                           * differ in the last bits: keep it fixed for runs that must agree bitwise.             */
     double L;             /* domain length                                                         */
     double dt;            /* time step                                                             */
 } mpde_config;

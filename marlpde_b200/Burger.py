@@ -25,7 +25,7 @@ class Burger(SpectralEnv):
     def __init__(self, L=2. * np.pi, N=1024, dt=0.001, nu=0.02, dforce=True, ssmforce=False, nsteps=None,
                  tend=5., u0=None, v0=None, case=None, forcing=False, ssm=False, dsm=False, noise=0., seed=42,
                  version=0, nunoise=False, numAgents=1, s=1, *, nenvs=1, device=None, dtype=torch.float64,
-                 history=None, offset=None):
+                 history=None, offset=None, team_lanes=0):
         assert not (ssm and dsm)                                            # Burger.py:50
         if ssmforce and not dforce:
             raise SystemExit("[Burger] SSM forcing requires dforce")      # Burger.py:113-115
@@ -87,7 +87,7 @@ class Burger(SpectralEnv):
 
         flags = (L_DFORCE if dforce else 0) | (L_FORCING if forcing else 0) | (L_SSM if ssm else 0) | (L_DSM if dsm else 0)
         self._create(nenvs=B, N=N, L_=self.L, dt=self.dt, M=0, num_agents=numAgents, version=version,
-                     stepper=self.stepper, flags=flags, device=device, dtype=dtype)
+                     stepper=self.stepper, flags=flags, device=device, dtype=dtype, team_lanes=team_lanes)
         L_check(self._lib.mpde_set_nu(self._h, LB.as_dp(np.ascontiguousarray(self._nu)), B))
 
         self.k = fft_wavenumbers(self.L, N)                                # Burger.py:161-163

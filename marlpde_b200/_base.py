@@ -26,7 +26,7 @@ class BatchedEnv:
     equation = None
 
     def _create(self, *, nenvs, N, L_, dt, M=0, num_agents=1, version=0, stepper=1, flags=0,
-                reward_mode=L.REWARD_NONE, device=None, dtype=torch.float64):
+                reward_mode=L.REWARD_NONE, device=None, dtype=torch.float64, team_lanes=0):
         if not torch.cuda.is_available():
             raise RuntimeError("marlpde_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self._lib = L.lib()
@@ -50,6 +50,7 @@ class BatchedEnv:
         cfg.N, cfg.M, cfg.num_agents, cfg.version = int(N), int(M), int(num_agents), int(version)
         cfg.stepper, cfg.flags, cfg.reward_mode = int(stepper), int(flags), int(reward_mode)
         cfg.L, cfg.dt = float(L_), float(dt)
+        cfg.team_lanes = int(team_lanes or 0)
         h = C.c_void_p()
         L.check(self._lib.mpde_create(C.byref(cfg), C.byref(h)))
         self._h = h

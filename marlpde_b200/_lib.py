@@ -27,7 +27,7 @@ class MpdeConfig(C.Structure):
         ("struct_size", C.c_int32), ("equation", C.c_int32), ("dtype", C.c_int32), ("device", C.c_int32),
         ("nenvs", C.c_int64),
         ("N", C.c_int32), ("M", C.c_int32), ("num_agents", C.c_int32), ("version", C.c_int32),
-        ("stepper", C.c_int32), ("flags", C.c_int32), ("reward_mode", C.c_int32), ("reserved", C.c_int32),
+        ("stepper", C.c_int32), ("flags", C.c_int32), ("reward_mode", C.c_int32), ("team_lanes", C.c_int32),
         ("L", C.c_double), ("dt", C.c_double),
     ]
 

@@ -90,8 +90,10 @@ int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
 // the last bits, and environment e must give the same bits whether it runs alone or inside a batch of 65536.
 // Measured on B200, fp64 N = 32, B = 4096, 10 sub-steps: 16 lanes 15.2 us, 8 lanes 13.9 us, 4 lanes 14.7 us per launch
 // (the 4-lane shared-memory-transpose variant has the lowest per-step slope and wins from B ~ 8192 per GPU).
-// MPDE_TS selects another variant for the whole process (tuning / tests; not bitwise compatible with the default).
-inline int pick_team(int64_t /*B*/, int N, int ts_max, int ts_min) {
+// mpde_config.team_lanes (Burger(team_lanes=...)) or MPDE_TS (whole process: tuning / tests) select another variant;
+// not bitwise compatible with the default.
+inline int pick_team(int requested, int N, int ts_max, int ts_min) {
+    if (requested >= ts_min && requested <= ts_max && (requested & (requested - 1)) == 0) return requested;   // mpde_config.team_lanes
     if (const char* s = std::getenv("MPDE_TS")) {
         const int v = std::atoi(s);
         if (v >= ts_min && v <= ts_max && (v & (v - 1)) == 0) return v;

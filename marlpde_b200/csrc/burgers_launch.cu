@@ -5,7 +5,7 @@ namespace mpde {
 
 template <typename T>
 static int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st) {
-    switch (pick_team(p.B, 32, 16, 4)) {
+    switch (pick_team(p.team_lanes, 32, 16, 4)) {
         case 16: return launch_burgers_32_16<T>(p, st);
         case 8: return launch_burgers_32_8<T>(p, st);
         default: return launch_burgers_32_4<T>(p, st);
@@ -13,7 +13,7 @@ static int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st) {
 }
 template <typename T>
 static int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st) {
-    switch (pick_team(p.B, 64, 32, 8)) {
+    switch (pick_team(p.team_lanes, 64, 32, 8)) {
         case 32: return launch_burgers_64_32<T>(p, st);
         case 16: return launch_burgers_64_16<T>(p, st);
         default: return launch_burgers_64_8<T>(p, st);

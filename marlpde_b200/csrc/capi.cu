@@ -108,6 +108,7 @@ struct Env : mpde_env {
         prm.version = cfg.version;
         prm.stepper = cfg.stepper;
         prm.reward_mode = cfg.reward_mode;
+        prm.team_lanes = cfg.team_lanes;
         prm.dt = (T)cfg.dt;
         prm.dx = (T)(cfg.L / N);
         if (spectral()) {

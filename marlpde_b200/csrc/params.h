@@ -44,6 +44,7 @@ template <typename T>
 struct SpectralParams {
     int64_t B;
     int N, M, A, version, stepper, nsub, flags, reward_mode;
+    int team_lanes;         // 0 = default team size for this N (mpde_config.team_lanes)
     T dt, dx;
     // read-only tables
     const Cx<T>* tw;        // [N/2]  exp(-2 pi i j / N)

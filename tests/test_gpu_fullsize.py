@@ -98,6 +98,26 @@ def test_full_size_config5_marl_mse(team):
     assert rel(r1, expect.cpu().numpy()) < 1e-9
 
 
+def test_team_lanes_option_equals_env_override(golden, team):
+    """Burger(team_lanes=4) selects the 4-lane kernels for that handle only: same bits as MPDE_TS=4, and the default
+    handle next to it keeps the default team."""
+    g = golden("burger_steps.npz")
+    V, A = g["eddy_forced/v"], g["eddy_forced/actions"]
+    team(None)
+    a, _ = make_env("eddy_forced", g, B=5, history=False, team_lanes=4)
+    d, _ = make_env("eddy_forced", g, B=5, history=False)
+    team(4)
+    b, _ = make_env("eddy_forced", g, B=5, history=False)
+    for e in (a, b, d):
+        e.IC(v0=V[:5])
+    b.step_n(A[:5], 9, want_reward=False)
+    team(None)
+    a.step_n(A[:5], 9, want_reward=False)
+    d.step_n(A[:5], 9, want_reward=False)
+    assert torch.equal(a.v, b.v)
+    assert rel(a.v, d.v.cpu().numpy()) < 1e-12 and not torch.equal(a.v, d.v)
+
+
 def test_full_size_config3_ks(golden):
     """BASELINE config 3: 8192 KS environments, L = 22, N = 64, dt = 0.25, M = 64 hat basis."""
     from marlpde_b200 import KS
