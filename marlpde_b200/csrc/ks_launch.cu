@@ -20,8 +20,25 @@ static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
     return 1;
 }
 
+// lanes per environment for N = 64: mpde_config.team_lanes, else MPDE_KS_TS (tuning), else the default
+static int ks_team(int requested, int dflt) {
+    if (requested == 8 || requested == 16 || requested == 32) return requested;
+    if (const char* s = std::getenv("MPDE_KS_TS")) {
+        const int v = std::atoi(s);
+        if (v == 8 || v == 16 || v == 32) return v;
+    }
+    return dflt;
+}
+
 template <typename T>
 int launch_ks(const SpectralParams<T>& p, cudaStream_t st) {
+    if (p.N == 64) {
+        switch (ks_team(p.team_lanes, 16)) {       // B200, 8192 envs, 10 steps: 32 lanes 122 us, 16 lanes 106 us, 8 lanes 109 us
+            case 8: return launch_ks_warp<T, 64, 8>(p, st);
+            case 32: return launch_ks_warp<T, 64, 32>(p, st);
+            default: return launch_ks_warp<T, 64, 16>(p, st);
+        }
+    }
     switch (p.N) {
         case 8: return launch_ks_warp<T, 8, 4>(p, st);
         case 16: return launch_ks_warp<T, 16, 8>(p, st);
