@@ -21,13 +21,13 @@ constexpr int min_blocks() {
 #endif
 constexpr int WARPS_PER_CTA = 2;
 
-template <typename T, int N, int TS, int SF, bool LEAN>
+template <typename T, int N, int TS, int SF, int LEAN>
 __global__ void __launch_bounds__(MPDE_LB) burgers_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BurgersWarp<T, N, TS, SF, LEAN>::run(prm, reinterpret_cast<T*>(smem_raw));
 }
 
-template <typename T, int N, int TS, int SF, bool LEAN = false>
+template <typename T, int N, int TS, int SF, int LEAN = 0>
 int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
     constexpr int TPW = 32 / TS;
     const int64_t warps = (p.B + TPW - 1) / TPW;
@@ -57,7 +57,10 @@ int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
 template <typename T, int N, int TS, int SF>
 int launch_warp_lean(const SpectralParams<T>& p, cudaStream_t st) {
     const bool lean = p.hist_rows == 0 && !(p.reward_mode == REWARD_MSE && p.truth) && p.stepper == 1 && p.version != 1;
-    return lean ? launch_warp<T, N, TS, SF, true>(p, st) : launch_warp<T, N, TS, SF, false>(p, st);
+    const bool hot = lean && p.nsub > 0 && p.state_out && p.A == 1 && (p.version == 0 || p.version == 2) &&
+                     !(p.flags & F_BASIS_DENSE) && p.reward_mode != REWARD_MSE;
+    if (hot) return launch_warp<T, N, TS, SF, 2>(p, st);
+    return lean ? launch_warp<T, N, TS, SF, 1>(p, st) : launch_warp<T, N, TS, SF, 0>(p, st);
 }
 template <typename T, int N, int TS>
 int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {

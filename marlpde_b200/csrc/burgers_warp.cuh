@@ -32,8 +32,13 @@ __device__ __forceinline__ float ek_row_f32(float re, float im, int N, float dxf
 // LEAN: compile-time promise of the common training configuration -- no history buffers, no MSE
 // truth table, forcing column period 1, state version != 1 (no dudt, so u_prev is not tracked) --
 // which removes those branches and registers from the sub-step loop.
-template <typename T, int N, int TS_, int SF, bool LEAN = false>
+// LEAN = 2 ("hot") additionally promises: every call advances (nsub > 0) and writes the state, one agent, state version 0
+// or 2 (per-point rows stored straight from registers), sparse (<= 2-tap) action basis, no MSE reward -- the cold
+// epilogue paths (shared-memory gather with integer divisions, dense basis product, MSE segments) are not even
+// compiled in, which shortens the once-per-launch code the instruction cache has to stream.
+template <typename T, int N, int TS_, int SF, int LEAN = 0>
 struct BurgersWarp {
+    static constexpr bool HOT = LEAN >= 2;
     using R = RealFFT<T, N, TS_>;
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
     // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row
@@ -102,7 +107,7 @@ struct BurgersWarp {
         const int64_t e = first + team;
         const bool has = e < prm.B;
         const int64_t ec = has ? e : 0;
-        const int flags = SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF);
+        const int flags = (SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF)) & (HOT ? ~(F_NO_ADVANCE | F_BASIS_DENSE) : ~0);
         const bool q1 = !(flags & F_FORCING);
         T* scratch = team_smem + 2 * R::SMEM_CX;
         T* stash = scratch + work_doubles(prm.M);      // per-team constants parked in shared memory (register relief)
@@ -536,7 +541,7 @@ struct BurgersWarp {
         const int64_t poff = prm.peer.parity * prm.peer.parity_stride;
         T* const state_out = prm.state_out ? prm.state_out + poff : nullptr;
         T* const reward_out = prm.reward_out ? prm.reward_out + poff : nullptr;
-        if (prm.state_out && prm.A == 1 && prm.version <= 2) {
+        if (HOT || (prm.state_out && prm.A == 1 && prm.version <= 2)) {
             // getState, single agent, versions 0/1/2 (Burger.py:617-622): rows are per-point fields, so the
             // lane's two adjacent points go out as one 16-byte store each -- no shared-memory gather
             const int ver = (LEAN && prm.version == 1) ? 0 : prm.version;
@@ -573,7 +578,7 @@ struct BurgersWarp {
                     }
                 }
             }
-        } else if (prm.state_out) {
+        } else if (!HOT && prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store
             const int ver = (LEAN && prm.version == 1) ? 0 : prm.version, A = prm.A;
@@ -656,7 +661,7 @@ struct BurgersWarp {
                 if (f.dc && live) prm.kprev[e] = part;
             }
         }
-        if (prm.reward_out && prm.reward_mode == REWARD_MSE && prm.truth) {
+        if (!HOT && prm.reward_out && prm.reward_mode == REWARD_MSE && prm.truth) {
             const int A = prm.A, W = N / A;
             if (nsub == 0) {             // getMseReward() of the current state (Burger.py:578-601)
                 const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
