@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
-    ap.add_argument("--depth", type=int, default=4, help="e2e: independent batches in flight")
+    ap.add_argument("--depth", type=int, default=8, help="e2e: independent batches in flight")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")

@@ -303,19 +303,24 @@ class Burger(SpectralEnv):
             self._reward_at = self.ioutnum
         return st, rw
 
-    def step_n_host(self, actions_host, n, state_host, reward_host=None, stream=None):
+    def step_n_host(self, actions_host, n, state_host, reward_host=None, stream=None, packed_out=None):
         """Host-buffer form of step_n for a host-side policy: (pinned) host actions [B,M] in, (pinned) host
         state [B,S] / reward [B,A] out, everything enqueued asynchronously on ``stream`` (default: the current
-        stream) by ONE library call (H2D copy -> step kernel -> D2H copies).  Results are valid after the
-        stream / an event recorded behind this call completes."""
+        stream) by ONE library call (H2D copy -> step kernel -> D2H copies, replayed from a cached CUDA graph).
+        ``packed_out``: one pinned buffer [B*S | B*A] instead of state_host / reward_host -- a single D2H copy.
+        Results are valid after the stream / an event recorded behind this call completes."""
         self._upload_forcing()
-        for t_ in (actions_host, state_host, reward_host):
+        for t_ in (actions_host, state_host, reward_host, packed_out):
             assert t_ is None or (not t_.is_cuda and t_.is_contiguous() and t_.dtype == self.dtype)
         st = stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        have_rw = reward_host is not None and (self._spec_ref is not None or self._truth_shift is not None)
-        L_check(self._lib.mpde_step_host(self._h, actions_host.data_ptr() if actions_host is not None else None, int(n),
-                                         state_host.data_ptr() if state_host is not None else None,
-                                         reward_host.data_ptr() if have_rw else None, st))
+        have_rw = self._spec_ref is not None or self._truth_shift is not None
+        a_ptr = actions_host.data_ptr() if actions_host is not None else None
+        if packed_out is not None:
+            assert have_rw and packed_out.numel() == self.nenvs * (self._state_size + self._reward_buf.shape[1])
+            L_check(self._lib.mpde_step_host_packed(self._h, a_ptr, int(n), packed_out.data_ptr(), st))
+        else:
+            L_check(self._lib.mpde_step_host(self._h, a_ptr, int(n), state_host.data_ptr() if state_host is not None else None,
+                                             reward_host.data_ptr() if (have_rw and reward_host is not None) else None, st))
         self.stepnum += n
         self.ioutnum += n
         for _ in range(n):

@@ -53,6 +53,7 @@ struct mpde_env {
                                  const uint8_t* mask, cudaStream_t st) = 0;
     virtual int step(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
     virtual int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) = 0;
+    virtual int step_host_packed(const void* actions, int nsub, void* out, cudaStream_t st) = 0;
     virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
                                 void* mc_reward) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
@@ -408,19 +409,28 @@ struct Env : mpde_env {
     }
 
     // host-buffer variant: stage through library-owned device buffers (allocated on first use)
-    T *stage_act = nullptr, *stage_state = nullptr, *stage_reward = nullptr;
-    size_t stage_act_n = 0, stage_state_n = 0, stage_reward_n = 0;
+    // state and reward staging are ONE device allocation [state | reward]: when the caller's host buffers are laid out
+    // the same way (reward right behind the state) both travel in a single D2H copy
+    bool packed_out = false;      // set by mpde_step_host_packed for the duration of the call
+    T *stage_act = nullptr, *stage_out = nullptr;
+    size_t stage_act_n = 0, stage_out_n = 0;
     // The chain H2D -> kernel -> D2H of one (actions, nsub, state, reward) signature is captured ONCE into a CUDA
     // graph and replayed by later calls: one driver call per RL step instead of four (MPDE_HOST_GRAPH=0 disables;
     // a stream that is already being captured by the caller, or the legacy default stream, gets the plain chain).
     struct HostGraph {
-        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec;
+        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec; bool packed;
     };
     std::vector<HostGraph> host_graphs;
     int step_host_enqueue(const void* actions, int nsub, void* state_out, void* reward_out, size_t na, size_t ns, size_t nr,
                           cudaStream_t st) {
+        T* const stage_state = stage_out;
+        T* const stage_reward = stage_out + ns;
         if (na) CU(cudaMemcpyAsync(stage_act, actions, na * sizeof(T), cudaMemcpyHostToDevice, st));
         if (step(na ? stage_act : nullptr, nsub, ns ? stage_state : nullptr, nr ? stage_reward : nullptr, st)) return -1;
+        if (ns && nr && packed_out && reward_out == static_cast<T*>(state_out) + ns) {
+            CU(cudaMemcpyAsync(state_out, stage_state, (ns + nr) * sizeof(T), cudaMemcpyDeviceToHost, st));
+            return 0;
+        }
         if (ns) CU(cudaMemcpyAsync(state_out, stage_state, ns * sizeof(T), cudaMemcpyDeviceToHost, st));
         if (nr) CU(cudaMemcpyAsync(reward_out, stage_reward, nr * sizeof(T), cudaMemcpyDeviceToHost, st));
         return 0;
@@ -433,15 +443,15 @@ struct Env : mpde_env {
         const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
         const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
         if (na > stage_act_n) { if (dalloc(&stage_act, na)) return -1; stage_act_n = na; ++epoch; }
-        if (ns > stage_state_n) { if (dalloc(&stage_state, ns)) return -1; stage_state_n = ns; ++epoch; }
-        if (nr > stage_reward_n) { if (dalloc(&stage_reward, nr)) return -1; stage_reward_n = nr; ++epoch; }
+        if (ns + nr > stage_out_n) { if (dalloc(&stage_out, ns + nr + 2)) return -1; stage_out_n = ns + nr; ++epoch; }
         static const bool use_graph = [] { const char* s = std::getenv("MPDE_HOST_GRAPH"); return !(s && s[0] == '0'); }();
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (st) CU(cudaStreamIsCapturing(st, &cs));
         if (!use_graph || !st || st == cudaStreamLegacy || cs != cudaStreamCaptureStatusNone)
             return step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
         for (const HostGraph& g : host_graphs)
-            if (g.actions == actions && g.state == state_out && g.reward == reward_out && g.nsub == nsub && g.epoch == epoch) {
+            if (g.actions == actions && g.state == state_out && g.reward == reward_out && g.nsub == nsub && g.epoch == epoch &&
+                g.packed == packed_out) {
                 CU(cudaGraphLaunch(g.exec, st));
                 launches += g.kernels;
                 return 0;
@@ -467,10 +477,20 @@ struct Env : mpde_env {
             cudaGraphExecDestroy(host_graphs.front().exec);
             host_graphs.erase(host_graphs.begin());
         }
-        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec});
+        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec, packed_out});
         CU(cudaGraphLaunch(exec, st));
         launches += kernels;
         return 0;
+    }
+
+    int step_host_packed(const void* actions, int nsub, void* out, cudaStream_t st) override {
+        if (!out) return fail("step_host_packed: null output buffer");
+        const size_t ns = (size_t)cfg.nenvs * (size_t)state_size();
+        const bool has_reward = cfg.reward_mode != MPDE_REWARD_NONE && nsub > 0;
+        packed_out = true;
+        const int rc = step_host(actions, nsub, out, has_reward ? static_cast<T*>(out) + ns : nullptr, st);
+        packed_out = false;
+        return rc;
     }
 
     int get(int field, void* dst, cudaStream_t st) override {
@@ -649,6 +669,9 @@ int mpde_step(mpde_env* env, const void* actions, int32_t nsub, void* state_out,
 }
 int mpde_step_host(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, void* stream) {
     return env ? env->step_host(actions, nsub, state_out, reward_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_step_host_packed(mpde_env* env, const void* actions, int32_t nsub, void* out_host, void* stream) {
+    return env ? env->step_host_packed(actions, nsub, out_host, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
 int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride,
                          void* mc_state, void* mc_reward) {

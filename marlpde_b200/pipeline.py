@@ -21,8 +21,10 @@ class HostPipeline:
         self.done = [torch.cuda.Event() for _ in self.envs]
         self.act_host = [torch.empty((B, M), dtype=dt).pin_memory() for _ in self.envs]
         self.act_dev = [torch.empty((B, M), dtype=dt, device=dev) for _ in self.envs]
-        self.state_host = [torch.empty((B, S), dtype=dt).pin_memory() for _ in self.envs]
-        self.reward_host = [torch.empty((B, A), dtype=dt).pin_memory() for _ in self.envs]
+        # state and reward share ONE pinned buffer [B*S | B*A]: the library then returns both in a single D2H copy
+        self.out_host = [torch.empty(B * (S + A), dtype=dt).pin_memory() for _ in self.envs]
+        self.state_host = [o[:B * S].view(B, S) for o in self.out_host]
+        self.reward_host = [o[B * S:].view(B, A) for o in self.out_host]
         self.h2d_bytes = self.act_host[0].numel() * self.act_host[0].element_size()
         self.d2h_bytes = (self.state_host[0].numel() + self.reward_host[0].numel()) * self.state_host[0].element_size()
         self.pending = [False] * len(self.envs)
@@ -33,8 +35,10 @@ class HostPipeline:
             self.act_host[k].copy_(torch.as_tensor(actions_host))
         if self.post_step is None and hasattr(self.envs[k], "step_n_host"):
             # one library call enqueues H2D -> kernel -> D2H on this slot's stream
-            self.envs[k].step_n_host(self.act_host[k], self.n_sub, self.state_host[k], self.reward_host[k],
-                                     stream=self.streams[k])
+            env = self.envs[k]
+            packed = self.out_host[k] if (env._spec_ref is not None or env._truth_shift is not None) else None
+            env.step_n_host(self.act_host[k], self.n_sub, self.state_host[k], self.reward_host[k], stream=self.streams[k],
+                            packed_out=packed)
             self.done[k].record(self.streams[k])
         else:
             with torch.cuda.stream(self.streams[k]):
