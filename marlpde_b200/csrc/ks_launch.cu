@@ -4,19 +4,33 @@
 
 namespace mpde {
 
-template <typename T, int N, int TS>
-__global__ void __launch_bounds__(64) ks_warp_kernel(const SpectralParams<T> prm) {
+// MINB = CTAs (of 64 threads) per SM the register allocation must allow: a batch of thousands of environments runs in
+// several waves, so more resident warps (fewer waves) beats more registers per thread
+template <typename T, int N, int TS, int MINB = 1>
+__global__ void __launch_bounds__(64, MINB) ks_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KSWarp<T, N, TS>::run(prm, reinterpret_cast<T*>(smem_raw));
 }
 
-template <typename T, int N, int TS>
+template <typename T, int N, int TS, int MINB = 1>
 static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
     constexpr int TPW = 32 / TS;
     const int64_t warps = (p.B + TPW - 1) / TPW;
     const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
-    const size_t smem = (size_t)2 * TPW * scr * sizeof(T);
-    ks_warp_kernel<T, N, TS><<<(int)((warps + 1) / 2), 64, smem, st>>>(p);
+    const size_t smem = ((size_t)2 * TPW * scr + 7 * (N / 2 + 1)) * sizeof(T);      // team scratch + shared ETDRK4 tables
+    // programmatic dependent launch, as for the Burgers kernels (the kernel reads mutable state after pdl_wait())
+    static const bool pdl = [] { const char* s = std::getenv("MPDE_PDL"); return !(s && s[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((warps + 1) / 2));
+    cfg.blockDim = dim3(64);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, ks_warp_kernel<T, N, TS, MINB>, p);
     return 1;
 }
 
@@ -36,7 +50,13 @@ int launch_ks(const SpectralParams<T>& p, cudaStream_t st) {
         switch (ks_team(p.team_lanes, 16)) {       // B200, 8192 envs, 10 steps: 32 lanes 122 us, 16 lanes 106 us, 8 lanes 109 us
             case 8: return launch_ks_warp<T, 64, 8>(p, st);
             case 32: return launch_ks_warp<T, 64, 32>(p, st);
-            default: return launch_ks_warp<T, 64, 16>(p, st);
+            default: {      // B200, 8192 envs, 10 steps: 236 regs 108.8 us, 168 regs 110.9 us, 128 regs (some spills) 99.5 us
+                int minb = 8;
+                if (const char* s = std::getenv("MPDE_KS_MINB")) minb = std::atoi(s);
+                if (minb == 6) return launch_ks_warp<T, 64, 16, 6>(p, st);
+                if (minb == 1) return launch_ks_warp<T, 64, 16, 1>(p, st);
+                return launch_ks_warp<T, 64, 16, 8>(p, st);
+            }
         }
     }
     switch (p.N) {

@@ -28,6 +28,16 @@ struct KSWarp {
 
     __device__ static void run(const SpectralParams<T>& prm, T* smem) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+        // ETDRK4 tables of the half spectrum, shared by every environment of the CTA: [7][H+1] = E, E2, Q, f1, f2, f3, -k/2
+        // (read from shared memory at each use instead of living in 7 P registers per lane: fewer registers, more
+        // resident warps, fewer waves)
+        constexpr int TW = H + 1;
+        T* const tab = smem + (size_t)wpc * TPW * max(prm.M, 2 * N + N / 2);
+        for (int i = threadIdx.x; i < 7 * TW; i += blockDim.x) {
+            const int t = i / TW, k = i - t * TW;
+            tab[i] = t < 6 ? prm.etd[t * N + k] : T(-0.5) * prm.kwave[k];
+        }
+        __syncthreads();
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
         if (first >= prm.B) return;
         R f;
@@ -43,24 +53,18 @@ struct KSWarp {
         const T dt = prm.dt, invN = T(1) / T(N);
 
         int kk[P];
-        T E[P], E2[P], Q[P], f1[P], f2[P], f3[P], gk[P];      // gk = -k/2: N(w) = g fft(u^2), g = -i k / 2
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            kk[p] = f.k(p);
-            E[p] = prm.etd[0 * N + kk[p]];
-            E2[p] = prm.etd[1 * N + kk[p]];
-            Q[p] = prm.etd[2 * N + kk[p]];
-            f1[p] = prm.etd[3 * N + kk[p]];
-            f2[p] = prm.etd[4 * N + kk[p]];
-            f3[p] = prm.etd[5 * N + kk[p]];
-            gk[p] = T(-0.5) * prm.kwave[kk[p]];
-        }
-        const T EN = prm.etd[0 * N + H], E2N = prm.etd[1 * N + H], f1N = prm.etd[3 * N + H], f2N = prm.etd[4 * N + H],
-                f3N = prm.etd[5 * N + H], gN = T(-0.5) * prm.kwave[H];
+        for (int p = 0; p < P; ++p) kk[p] = f.k(p);
+        // table t at the wavenumber of register p / at the Nyquist mode; gk = -k/2: N(w) = g fft(u^2), g = -i k / 2
+        auto tb = [&](int t, int p) { return tab[t * TW + kk[p]]; };
+        auto tbN = [&](int t) { return tab[t * TW + H]; };
+        enum { TE = 0, TE2 = 1, TQ = 2, TF1 = 3, TF2 = 4, TF3 = 5, TG = 6 };
         Cx<T> ws_nl[P], ws1[P];
         f.scaled_twiddles(invN * invN, ws_nl);
         f.scaled_twiddles(T(1), ws1);
 
+        pdl_wait();                  // everything above reads constant tables only
+        pdl_launch_dependents();
         const bool was_live = has && prm.status[ec] == 0;
         bool live = was_live;
         int iout = prm.iout[ec];
@@ -133,8 +137,11 @@ struct KSWarp {
             for (int p = 0; p < P; ++p) z[p] = cx<T>(z[p].re * z[p].re, z[p].im * z[p].im);
             f.fwd(z, X, XN, invN * invN, ws_nl);
 #pragma unroll
-            for (int p = 0; p < P; ++p) out[p] = cx<T>(-gk[p] * X[p].im, gk[p] * X[p].re);     // (i gk) X, gk = -k/2
-            outNim = gN * XN;
+            for (int p = 0; p < P; ++p) {
+                const T g = tb(TG, p);
+                out[p] = cx<T>(-g * X[p].im, g * X[p].re);     // (i gk) X, gk = -k/2
+            }
+            outNim = tbN(TG) * XN;
         };
 
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
@@ -164,30 +171,41 @@ struct KSWarp {
             T NvN, NaN, NbN, NcN;
             nonlinear(v, vN.re, Nv, NvN);
 #pragma unroll
-            for (int p = 0; p < P; ++p) a[p] = cx<T>(fma(E2[p], v[p].re, Q[p] * Nv[p].re), fma(E2[p], v[p].im, Q[p] * Nv[p].im));
+            for (int p = 0; p < P; ++p) {
+                const T e2 = tb(TE2, p), q = tb(TQ, p);
+                a[p] = cx<T>(fma(e2, v[p].re, q * Nv[p].re), fma(e2, v[p].im, q * Nv[p].im));
+            }
+            const T E2N = tbN(TE2);
             const T aNre = E2N * vN.re;                  // the Nyquist entry of N(.) is purely imaginary
             nonlinear(a, aNre, Na, NaN);
 #pragma unroll
-            for (int p = 0; p < P; ++p) b[p] = cx<T>(fma(E2[p], v[p].re, Q[p] * Na[p].re), fma(E2[p], v[p].im, Q[p] * Na[p].im));
+            for (int p = 0; p < P; ++p) {
+                const T e2 = tb(TE2, p), q = tb(TQ, p);
+                b[p] = cx<T>(fma(e2, v[p].re, q * Na[p].re), fma(e2, v[p].im, q * Na[p].im));
+            }
             nonlinear(b, aNre, Nb, NbN);
 #pragma unroll
-            for (int p = 0; p < P; ++p)       // c = E2 a + Q (2 Nb - Nv), reusing b
-                b[p] = cx<T>(fma(E2[p], a[p].re, Q[p] * (T(2) * Nb[p].re - Nv[p].re)),
-                             fma(E2[p], a[p].im, Q[p] * (T(2) * Nb[p].im - Nv[p].im)));
+            for (int p = 0; p < P; ++p) {     // c = E2 a + Q (2 Nb - Nv), reusing b
+                const T e2 = tb(TE2, p), q = tb(TQ, p);
+                b[p] = cx<T>(fma(e2, a[p].re, q * (T(2) * Nb[p].re - Nv[p].re)),
+                             fma(e2, a[p].im, q * (T(2) * Nb[p].im - Nv[p].im)));
+            }
             nonlinear(b, E2N * aNre, Nc, NcN);
             // v <- E v + (Nv + F) f1 + 2 (Na + Nb + 2 F) f2 + (Nc + F) f3   (KS.py:265)
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                v[p] = cx<T>(E[p] * v[p].re + (Nv[p].re + F[p].re) * f1[p] + T(2) * (Na[p].re + Nb[p].re + T(2) * F[p].re) * f2[p] +
-                                 (Nc[p].re + F[p].re) * f3[p],
-                             E[p] * v[p].im + (Nv[p].im + F[p].im) * f1[p] + T(2) * (Na[p].im + Nb[p].im + T(2) * F[p].im) * f2[p] +
-                                 (Nc[p].im + F[p].im) * f3[p]);
+                const T Ep = tb(TE, p), f1p = tb(TF1, p), f2p = tb(TF2, p), f3p = tb(TF3, p);
+                v[p] = cx<T>(Ep * v[p].re + (Nv[p].re + F[p].re) * f1p + T(2) * (Na[p].re + Nb[p].re + T(2) * F[p].re) * f2p +
+                                 (Nc[p].re + F[p].re) * f3p,
+                             Ep * v[p].im + (Nv[p].im + F[p].im) * f1p + T(2) * (Na[p].im + Nb[p].im + T(2) * F[p].im) * f2p +
+                                 (Nc[p].im + F[p].im) * f3p);
                 bad |= blown(v[p]);
             }
+            const T EN = tbN(TE), f1N = tbN(TF1), f2N = tbN(TF2), f3N = tbN(TF3);
             vN = cx<T>(EN * vN.re + FN * f1N + T(2) * (T(2) * FN) * f2N + FN * f3N,
                        EN * vN.im + NvN * f1N + T(2) * (NaN + NbN) * f2N + NcN * f3N);
             if (f.dc) {
-                v[0].im = E[0] * v0im;
+                v[0].im = tb(TE, 0) * v0im;
                 bad |= blown(vN);
             }
             iout += 1;
