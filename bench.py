@@ -157,9 +157,13 @@ def reference_arm(args):
 
 
 def workload_config(n_gpus, transport=None):
-    return {"workload": f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
-                        f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
-                        f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of the batch",
+    what = (f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
+            f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
+            f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of the batch")
+    if WORKLOAD == "c5":
+        what = (f"MARL Burgers N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[4]), fp64, {N} per-gridpoint agents (state windows "
+                f"of 3, one eddy-viscosity action each), MSE reward vs a shared truth table, nIntermediate={NSUB}; 4-lane teams")
+    return {"workload": what,
             "envs_per_gpu": B_PER_GPU, "N": N, "M": M, "n_intermediate": NSUB, "global_envs": B_PER_GPU * n_gpus,
             "l2": f"rotating pool of {POOL} independent batches per GPU (state working set > 126 MB L2)",
             "parallelism": (f"env-sharded x{n_gpus}, state+reward gathered to every rank per RL step by {transport or 'peer'} "
@@ -167,7 +171,24 @@ def workload_config(n_gpus, transport=None):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+WORKLOAD = "c2"            # --workload c5 switches to BASELINE configs[4] per GPU (diagnostic; the bench line is c2)
+
+
+def make_batch_c5(torch, device, seed0):
+    """BASELINE configs[4] per GPU: MARL Burgers N=32, 32 per-gridpoint agents (state windows of 3, one action each),
+    MSE reward against a shared truth table, 4-lane teams (the large-batch kernel)."""
+    from marlpde_b200 import Burger
+    seeds = np.array(STABLE_SEEDS)[(np.arange(B_PER_GPU) + seed0) % len(STABLE_SEEDS)]
+    env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=False, dforce=False, seed=seeds, version=0,
+                 numAgents=N, nenvs=B_PER_GPU, device=device, history=False, team_lanes=4)
+    env.setup_basis(M, "hat")
+    env.set_truth_table(np.random.default_rng(seed0).normal(1.0, 0.3, (int(TEND / DT) + 1, N))[None])
+    return env
+
+
 def make_batch(torch, device, seed0):
+    if WORKLOAD == "c5":
+        return make_batch_c5(torch, device, seed0)
     from marlpde_b200 import Burger
     # forced N=32 LES blows up for most forcing seeds within ~10^3 steps (the reference's own physics);
     # these four stay bounded for a whole episode under a positive eddy viscosity, so every
@@ -199,6 +220,7 @@ def gpu_arm(args):
     acts_host = torch.from_numpy(np.repeat(rng.uniform(0.05, 0.1, (pool, B_PER_GPU, 1)), M, axis=2).copy()).pin_memory()
     acts = acts_host.to(device)
     S = envs[0]._state_size
+    RW = envs[0]._reward_buf.shape[1]
     gathers = []
     fused = world > 1 or args.fused_single      # --fused-single: 1-GPU diagnostic of the fused-gather overheads
     if fused:
@@ -207,8 +229,8 @@ def gpu_arm(args):
         # is the consumer side.  No NCCL call and no host work per step (marlpde_b200.dist.PeerGather.fuse).
         from marlpde_b200.dist import PeerGather
         for env in envs:
-            pg = PeerGather(B_PER_GPU * (S + 1), torch.float64, device, copies=2)
-            pg.fuse(env, B_PER_GPU, S, 1)
+            pg = PeerGather(B_PER_GPU * (S + RW), torch.float64, device, copies=2)
+            pg.fuse(env, B_PER_GPU, S, RW)
             gathers.append(pg)
 
     side = torch.cuda.Stream(device=device) if fused else None
@@ -242,19 +264,42 @@ def gpu_arm(args):
     graph, per_graph = None, 0
     rot = pool * (2 if fused else 1)        # steps per graph: both copies of the double-buffered gather when fused
     extra = 1 if fused and not args.no_wait else 0      # signal+wait kernel per step
+
+    def capture(chains):
+        """Graph of one rotation.  chains > 1: independent batches alternate between `chains` streams inside the graph, so
+        one batch's tail (and, multi-GPU, its gather stores draining over NVLink) overlaps the next batch's kernel; a single
+        chain serialises them (each kernel waits, through programmatic dependent launch, for its COMPLETE predecessor)."""
+        l_before = sum(e.launch_count for e in envs)
+        g_ = torch.cuda.CUDAGraph()
+        cstreams = [torch.cuda.Stream(device=device) for _ in range(chains)] if chains > 1 else []
+        with torch.cuda.graph(g_):
+            cap = torch.cuda.current_stream()
+            for cs in cstreams:
+                cs.wait_stream(cap)
+            for i in range(rot):
+                if chains > 1:
+                    with torch.cuda.stream(cstreams[i % chains]):
+                        one_step(i, join=False)
+                else:
+                    one_step(i, join=(i == rot - 1))
+            for cs in cstreams:
+                cap.wait_stream(cs)
+            if chains > 1 and fused and not args.no_wait:
+                cap.wait_stream(side)
+        n_k = (sum(e.launch_count for e in envs) - l_before) + extra * rot
+        for g in gathers:                   # the capture pass only recorded: no step was published
+            g.step -= rot // pool
+        torch.cuda.synchronize()
+        return g_, n_k
+
+    chains = max(1, args.chains)
+    if pool % chains:
+        chains = 1
     if args.graph:
         for i in range(rot):                # warm every batch before capture
             one_step(i)
         sync()
-        l_before = sum(e.launch_count for e in envs)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for i in range(rot):
-                one_step(i, join=(i == rot - 1))
-        per_graph = (sum(e.launch_count for e in envs) - l_before) + extra * rot
-        for g in gathers:                   # the capture pass only recorded: no step was published
-            g.step -= rot // pool
-        torch.cuda.synchronize()
+        graph, per_graph = capture(chains)
 
     def run_steps(first, n):
         """n RL steps starting at rotation index `first` (a multiple of pool when the graph is used)."""
@@ -285,6 +330,20 @@ def gpu_arm(args):
     ms = ev0.elapsed_time(ev1)
     for g in gathers:
         g.check()
+    # extra (not the headline): the same K steps with TWO independent batches in flight inside the graph
+    ms2 = None
+    if args.graph and chains == 1 and pool % 2 == 0 and K >= rot:
+        graph1, per1 = graph, per_graph
+        graph, per_graph = capture(2)
+        run_steps(0, rot)
+        sync()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        run_steps(0, K - K % rot)
+        ev3.record()
+        sync()
+        ms2 = ev2.elapsed_time(ev3) / (K - K % rot)
+        graph, per_graph = graph1, per1
     alive = all(int((e.status != 0).sum()) == 0 for e in envs)
 
     # ---- end to end through the public API with HOST buffers --------------------------------
@@ -301,7 +360,7 @@ def gpu_arm(args):
         g.step += 1
         g.exchange_next()
         mine = g.current()[rank]
-        return mine[:B_PER_GPU * S].view(B_PER_GPU, S), mine[B_PER_GPU * S:].view(B_PER_GPU, 1)
+        return mine[:B_PER_GPU * S].view(B_PER_GPU, S), mine[B_PER_GPU * S:].view(B_PER_GPU, RW)
 
     pipe = HostPipeline(envs[:depth], NSUB, post_step=gather if fused else None)
     for k in range(depth):
@@ -327,9 +386,10 @@ def gpu_arm(args):
     clocks = sampler.stop() if sampler else None
 
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3], device=device, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s * 1e3, ms2 or 0.0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+        ms2 = float(t[2]) if ms2 is not None else None
         ok = torch.tensor([1 if alive else 0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         alive = bool(ok.item())
@@ -367,6 +427,10 @@ def gpu_arm(args):
                               "peak_source": "measured (tools/microbench.cu DFMA loop)",
                               "note": "2.6 kflop per env-step (SURVEY 8d) x 40960 env-steps per launch"},
             "all_envs_alive": alive,
+            "two_batches_in_flight": None if ms2 is None else {
+                "ms_per_step": ms2, "value": total_envs * NSUB / (ms2 * 1e-3), "unit": "env-steps/s",
+                "note": "same steps with two independent batches alternating between two streams inside the replayed graph "
+                        "(one batch's tail overlaps the next batch's kernel); not used for value / roofline"},
         }
         if world == 1 and not args.no_cpu:
             v, cores, steps, wall = cpu_run(seconds=args.cpu_seconds)
@@ -392,7 +456,13 @@ def main():
     ap.add_argument("--no-wait", action="store_true", help="diagnostic: skip the consumer-side wait kernels")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of "
                     "replaying the captured pool rotation")
+    ap.add_argument("--chains", type=int, default=1, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        global WORKLOAD, B_PER_GPU, BYTES_PER_ENV_LAUNCH
+        WORKLOAD, B_PER_GPU = "c5", 8192
+        BYTES_PER_ENV_LAUNCH = 8 * (M + 4 * (N + 2) + 3 * N + N)        # 2368 B
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -124,3 +124,55 @@ def test_host_step_graph_replay_matches_plain_chain():
         torch.cuda.synchronize()
         assert torch.equal(st_h, st.cpu()) and torch.equal(rw_h, rw.cpu()), k
     assert env.launch_count - l0 == 4
+
+
+def _marl_factory(n, ids):
+    from marlpde_b200 import Burger
+    env = Burger(N=N, dt=1e-3, nu=0.02, tend=1.0, case="turbulence", forcing=False, dforce=False, seed=50 + (ids % 4) * 9,
+                 version=0, numAgents=N, nenvs=n, history=False)
+    env.setup_basis(M, "hat")
+    env.set_truth_table(np.random.default_rng(3).normal(1.0, 0.3, (1001, N))[None])
+    return env
+
+
+def _marl_worker(rank, ws, port, q):
+    import torch.distributed as dist
+    from marlpde_b200 import dist as mdist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    try:
+        sb = mdist.ShardedBatch(B, _marl_factory, transport="fused")
+        a = _acts().cuda()
+        for _ in range(3):
+            gs, gr = sb.step_n(a, 10)
+        torch.cuda.synchronize()
+        sb._peer.check()
+        q.put((rank, gs.cpu().numpy(), gr.cpu().numpy()))
+        sb._peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_marl_mse_fused_gather_bitwise():
+    """BASELINE config 5 in small: per-gridpoint agents (state windows through the shared-memory gather path, MSE reward per
+    agent), sharded over 2 GPUs with the fused gather == the same batch on one GPU, bitwise."""
+    import torch.multiprocessing as mp
+    ws, port = 2, 29500 + os.getpid() % 400 + 200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_marl_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in range(ws)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    torch.cuda.set_device(0)
+    env = _marl_factory(B, np.arange(B))
+    a = _acts().cuda()
+    for _ in range(3):
+        st, rw = env.step_n(a, 10)
+    for o in outs:
+        assert o[1].shape == (B, 3 * N) and o[2].shape == (B, N)
+        assert np.array_equal(o[1], st.cpu().numpy()) and np.array_equal(o[2], rw.cpu().numpy())
