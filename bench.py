@@ -230,7 +230,7 @@ def gpu_arm(args):
         from marlpde_b200.dist import PeerGather
         for env in envs:
             pg = PeerGather(B_PER_GPU * (S + RW), torch.float64, device, copies=2)
-            pg.fuse(env, B_PER_GPU, S, RW)
+            pg.fuse(env, B_PER_GPU, S, RW, gather_state=not args.rewards_only)
             gathers.append(pg)
 
     side = torch.cuda.Stream(device=device) if fused else None
@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of "
                     "replaying the captured pool rotation")
     ap.add_argument("--chains", type=int, default=1, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--rewards-only", action="store_true", help="multi-GPU: gather only the rewards (configs[4] wording)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")
     args = ap.parse_args()
     if args.workload == "c5":

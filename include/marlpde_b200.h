@@ -209,7 +209,7 @@ const char* mpde_peer_last_error(void);
  * by the library on the host) writes every buffer -- the local state_out / reward_out included -- at an offset of
  * (s & 1) * parity_stride ELEMENTS, so a fast rank's next step never lands in rows a slower rank's learner is still
  * reading (a CUDA graph that replays steps of `env` must therefore hold an even number of them).
- * mc_state / mc_reward (both or neither): this rank's slab addressed through an NVSwitch MULTICAST mapping of the gather
+ * mc_state / mc_reward (both, or mc_reward alone = only the rewards are gathered, the state stays local): this rank's slab addressed through an NVSwitch MULTICAST mapping of the gather
  * buffers (cuMulticast* / torch symmetric memory): one multimem.st per row then reaches every rank, this one included,
  * replacing the local store and the per-peer loop (pass n_data = 0).
  * n_data = 0, parity_stride = 0 and no multicast pointers unbinds.

@@ -611,19 +611,34 @@ struct BurgersWarp {
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
             const int RL = nf * seg + tail;
             const int S = A * RL;
-            if (has) {
-                for (int o = tl; o < S; o += TS) {
-                    const int a = o / RL, r = o - a * RL;
-                    T val;
-                    if (r < nf * seg) {
-                        const int fld = r / seg, w = r - fld * seg;
-                        const int start = A == 1 ? 0 : a * (N / A) - 1;
-                        const int j = (start + w + N) & (N - 1);
-                        val = f0[fld * N + j];
+            auto element = [&](int o) {                                      // o-th number of this environment's state row
+                const int a = o / RL, r = o - a * RL;
+                T val;
+                if (r < nf * seg) {
+                    const int fld = r / seg, w = r - fld * seg;
+                    const int start = A == 1 ? 0 : a * (N / A) - 1;
+                    const int j = (start + w + N) & (N - 1);
+                    val = f0[fld * N + j];
+                } else {
+                    val = f0[2 * N + (r - nf * seg)];
+                }
+                return live ? val : inf;                                     // Burger.py:633-643
+            };
+            if (has && (S & 1) == 0) {
+                // rows of even length: two numbers per 16-byte store, the lanes of a team cover contiguous 16 TS bytes
+                for (int o = 2 * tl; o < S; o += 2 * TS) {
+                    const Cx<T> out = cx<T>(element(o), element(o + 1));
+                    if (prm.peer.mc_state) {
+                        st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o), out);
                     } else {
-                        val = f0[2 * N + (r - nf * seg)];
+                        stcx(reinterpret_cast<Cx<T>*>(state_out + e * S + o), out);
+                        for (int q = 0; q < prm.peer.n_data; ++q)
+                            stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + e * S + o), out);
                     }
-                    const T out = live ? val : inf;                        // Burger.py:633-643
+                }
+            } else if (has) {
+                for (int o = tl; o < S; o += TS) {
+                    const T out = element(o);
                     if (prm.peer.mc_state) {
                         st_multicast(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o, out);
                     } else {
@@ -677,11 +692,25 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) stcx(reinterpret_cast<Cx<T>*>(scratch) + p * TS + tl, mse[p]);
             __syncwarp(f.c.tmask);
-            if (has) {
-                for (int a = tl; a < A; a += TS) {       // agent a owns points [a N/A, (a+1) N/A)
-                    T sum = T(0);
-                    for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
-                    const T r = live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
+            auto agent_reward = [&](int a) {             // agent a owns points [a N/A, (a+1) N/A)
+                T sum = T(0);
+                for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
+                return live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
+            };
+            if (has && (A & 1) == 0) {                   // two agents per 16-byte store
+                for (int a = 2 * tl; a < A; a += 2 * TS) {
+                    const Cx<T> r = cx<T>(agent_reward(a), agent_reward(a + 1));
+                    if (prm.peer.mc_reward) {
+                        st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a), r);
+                    } else {
+                        stcx(reinterpret_cast<Cx<T>*>(reward_out + e * A + a), r);
+                        for (int q = 0; q < prm.peer.n_data; ++q)
+                            stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.reward[q]) + poff + e * A + a), r);
+                    }
+                }
+            } else if (has) {
+                for (int a = tl; a < A; a += TS) {
+                    const T r = agent_reward(a);
                     if (prm.peer.mc_reward) {
                         st_multicast(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a, r);
                     } else {

@@ -279,7 +279,7 @@ struct Env : mpde_env {
         peer_bound = false;
         peer_steps = 0;
         prm.peer = PeerSink{};
-        if (n_data == 0 && parity_stride == 0 && !mc_state) return 0;
+        if (n_data == 0 && parity_stride == 0 && !mc_state && !mc_reward) return 0;
         if (cfg.equation != MPDE_BURGERS || cfg.N > 256)
             return fail("set_peer_output: the fused gather exists for the warp-resident Burgers kernels (N <= 256) only; "
                         "use mpde_peer_put for the other solvers");
@@ -293,7 +293,8 @@ struct Env : mpde_env {
             ps.reward[i] = reward[i];
         }
         ps.parity_stride = parity_stride;
-        if ((mc_state == nullptr) != (mc_reward == nullptr)) return fail("set_peer_output: multicast needs both pointers");
+        if (mc_state && !mc_reward) return fail("set_peer_output: multicast of the state without the reward");
+        if (mc_reward && !mc_state && n_data > 0) return fail("set_peer_output: reward-only multicast takes n_data = 0");
         ps.mc_state = mc_state;
         ps.mc_reward = mc_reward;
         prm.peer = ps;

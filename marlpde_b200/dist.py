@@ -173,7 +173,7 @@ class PeerGather:
         self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err.data_ptr(), self.max_spins,
                                              self._stream()))
 
-    def fuse(self, env, n_local, S, A, use_multicast=True):
+    def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True):
         """Let ``env``'s step kernel write its [n_local,S] state and [n_local,A] reward straight into this rank's slab
         of every rank's buffer and publish the step itself (no put kernel, no NCCL)."""
         C = self._C
@@ -192,10 +192,14 @@ class PeerGather:
         import os
         if self.multicast_base and use_multicast and os.environ.get("MPDE_MULTICAST", "1") != "0":
             # one multimem.st per row reaches every rank (this one included): no per-peer stores at all
-            mc_state = self.multicast_base + slab
-            mc_reward = mc_state + n_local * S * self._item
+            mc_reward = self.multicast_base + slab + n_local * S * self._item
+            # gather_state=False: only the rewards travel (BASELINE configs[4]: "allgather of rewards"); the state rows
+            # are written into this rank's own slab only
+            mc_state = self.multicast_base + slab if gather_state else None
             others = []
-        self.multicast = mc_state is not None
+        if not gather_state and mc_reward is None:
+            raise RuntimeError("gather_state=False needs the multicast path (NVSwitch); use the full gather otherwise")
+        self.multicast = mc_reward is not None
         rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, stride, mc_state, mc_reward)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
