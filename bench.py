@@ -38,9 +38,9 @@ STABLE_SEEDS = (50, 59, 81, 89)
 BYTES_PER_ENV_LAUNCH = 8 * (M + 4 * (N + 2) + 6 + N + N + 1)
 FLOPS_PER_ENV_STEP = 2600           # algorithmic fp64 flops of one Burgers N=32 solver step
 FP64_PEAK_TFLOPS = 33.2             # measured on this pool's B200 with tools/microbench.cu (profiles/r1_microbench_b200.md)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary_b1.md): the reads
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary_final.md): the reads
 # are the cold-cache state + actions; the 3.6 MB of results are still dirty in the 126 MB L2 when the replay ends
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 3.957e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 3.951e6
 
 
 def peaks():
@@ -330,9 +330,18 @@ def gpu_arm(args):
     ms = ev0.elapsed_time(ev1)
     for g in gathers:
         g.check()
+    alive = all(int((e.status != 0).sum()) == 0 for e in envs)
+
+    def new_episode():
+        """Untimed: put every batch back at t = 0 (the forced N=32 LES only stays bounded for about one episode)."""
+        for e in envs:
+            e.IC(case="turbulence")
+        sync()
+
     # extra (not the headline): the same K steps with TWO independent batches in flight inside the graph
     ms2 = None
     if args.graph and chains == 1 and pool % 2 == 0 and K >= rot:
+        new_episode()
         graph1, per1 = graph, per_graph
         graph, per_graph = capture(2)
         run_steps(0, rot)
@@ -344,7 +353,8 @@ def gpu_arm(args):
         sync()
         ms2 = ev2.elapsed_time(ev3) / (K - K % rot)
         graph, per_graph = graph1, per1
-    alive = all(int((e.status != 0).sum()) == 0 for e in envs)
+        alive = alive and all(int((e.status != 0).sum()) == 0 for e in envs)
+    new_episode()
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     # Every RL step of every batch: pinned-host actions -> H2D -> step_n (one launch) -> D2H of state and
@@ -415,7 +425,7 @@ def gpu_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": how,
-                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,LEAN>",
+                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,HOT>",
                          "bytes_per_launch": B_PER_GPU * BYTES_PER_ENV_LAUNCH,
                          "launch_us": per_launch_s * 1e6,
                          "note": "algorithmic bytes = 1912 B per env per launch (SURVEY 8d) x 4096 envs; the 10 solver "

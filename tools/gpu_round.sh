@@ -9,9 +9,6 @@ python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest 
 tail -3 $out/${tag}_pytest.log
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 40 --warmup 3 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err; echo "ref rc=$?"
-for ts in 16 8; do
-  MPDE_TS=$ts python bench.py --steps 2400 --warmup 24 --no-cpu > $out/${tag}_bench_ts$ts.json 2>> $out/${tag}_bench.err
-done
 CMD="python bench.py --steps 96 --warmup 24 --no-cpu --pool 4 --no-graph"
 $CMD > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv $CMD > $out/${tag}_ncu1.log 2>&1
