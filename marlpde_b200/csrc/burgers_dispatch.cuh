@@ -8,8 +8,9 @@ namespace mpde {
 // Register budget.  CTAs are 64 threads (2 warps).  The hot case -- fp64, N = 32, 16 lanes per environment,
 // B = 4096 -> 2048 warps = 13.8 per SM -- must be resident in ONE wave: 7 CTAs per SM = 144 registers per thread
 // (at 128 ptxas shuffles 64-bit values through XOR swaps and moves: +50 instructions per sub-step).
-template <typename T, int N, int TS>
+template <typename T, int N, int TSTAG>
 constexpr int min_blocks() {
+    constexpr int TS = TSTAG < 0 ? -TSTAG : TSTAG;
     constexpr int P = N / 2 / TS;
     if (sizeof(T) == 8 && N == 32 && P == 1) return 7;
     return 4 * (sizeof(T) == 8 ? (P <= 1 ? 2 : 1) : (P <= 2 ? 2 : 1));
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(MPDE_LB) burgers_warp_kernel(const SpectralPar
 
 template <typename T, int N, int TS, int SF, int LEAN = 0>
 int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
-    constexpr int TPW = 32 / TS;
+    constexpr int TPW = BurgersWarp<T, N, TS, SF, LEAN>::TPW;
     const int64_t warps = (p.B + TPW - 1) / TPW;
     constexpr int wpc = WARPS_PER_CTA;
     const int block = 32 * wpc;
@@ -81,26 +82,31 @@ int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
 }
 
 // one translation unit per (N, team size): defines launch_burgers_<N>_<TS><T>
-#define MPDE_INSTANTIATE_TEAM(N_, TS_)                                                                         \
-    template <typename T> int launch_burgers_##N_##_##TS_(const SpectralParams<T>& p, cudaStream_t st) {      \
-        return launch_warp_sf<T, N_, TS_>(p, st);                                                              \
+#define MPDE_INSTANTIATE_TEAM_AS(N_, NAME_, TSTAG_)                                                            \
+    template <typename T> int launch_burgers_##N_##_##NAME_(const SpectralParams<T>& p, cudaStream_t st) {    \
+        return launch_warp_sf<T, N_, TSTAG_>(p, st);                                                           \
     }                                                                                                          \
-    template int launch_burgers_##N_##_##TS_<double>(const SpectralParams<double>&, cudaStream_t);            \
-    template int launch_burgers_##N_##_##TS_<float>(const SpectralParams<float>&, cudaStream_t);
+    template int launch_burgers_##N_##_##NAME_<double>(const SpectralParams<double>&, cudaStream_t);          \
+    template int launch_burgers_##N_##_##NAME_<float>(const SpectralParams<float>&, cudaStream_t);
+#define MPDE_INSTANTIATE_TEAM(N_, TS_) MPDE_INSTANTIATE_TEAM_AS(N_, TS_, TS_)
 
-// Team size = lanes per environment.  It is a function of N ONLY (two complex points per lane: N = 32 -> 8 lanes,
-// N = 64 -> 16 lanes), never of the batch size: the variants factor the FFT differently, so their results differ in
-// the last bits, and environment e must give the same bits whether it runs alone or inside a batch of 65536.
-// Measured on B200, fp64 N = 32, B = 4096, 10 sub-steps: 16 lanes 15.2 us, 8 lanes 13.9 us, 4 lanes 14.7 us per launch
-// (the 4-lane shared-memory-transpose variant has the lowest per-step slope and wins from B ~ 8192 per GPU).
-// mpde_config.team_lanes (Burger(team_lanes=...)) or MPDE_TS (whole process: tuning / tests) select another variant;
-// not bitwise compatible with the default.
-inline int pick_team(int requested, int N, int ts_max, int ts_min) {
-    if (requested >= ts_min && requested <= ts_max && (requested & (requested - 1)) == 0) return requested;   // mpde_config.team_lanes
-    if (const char* s = std::getenv("MPDE_TS")) {
-        const int v = std::atoi(s);
-        if (v >= ts_min && v <= ts_max && (v & (v - 1)) == 0) return v;
-    }
+// Team size = lanes per environment: a function of N ONLY by default (two complex points per lane: N = 32 -> 8 lanes,
+// N = 64 -> 16 lanes), never of the batch size, because the variants round differently and environment e must give the
+// same bits alone or inside a batch of 65536.  B200, fp64 N = 32, 10 fused sub-steps, us per launch:
+//   B = 4096: 16 lanes 14.8, 8 lanes 13.4, 4 lanes 13.9;  B = 8192: 24.2 / 25.7 / 19.5;  B = 32768: 86.6 / 89.9 / 64.0.
+// mpde_config.team_lanes (Burger(team_lanes=...)) or MPDE_TS (whole process) select a variant:
+//   4 / 8 / 16 : that many lanes;
+//   -8         : 8 lanes with the radix-2^2 shuffle network whose arithmetic is bit-identical to the 4-lane kernel
+//                (5 % slower than the plain 8-lane kernel: more selects);
+//   -1         : "consistent auto": -8 below ~6000 environments, 4 lanes above -- results do not depend on the batch size
+//                although the kernel does (N = 32, not with the dynamic Smagorinsky closure, whose means are summed in
+//                team order).
+inline int pick_team(int requested, int64_t B, int N, int flags, int ts_max, int ts_min) {
+    if (const char* s = std::getenv("MPDE_TS"))
+        if (requested == 0) requested = std::atoi(s);
+    if (N == 32 && requested == -1) return (B >= 6144 && !(flags & F_DSM)) ? 4 : -8;
+    if (N == 32 && requested == -8) return -8;
+    if (requested >= ts_min && requested <= ts_max && (requested & (requested - 1)) == 0) return requested;
     const int ts = N / 4;           // P = (N/2) / ts = 2 complex points per lane
     return ts > ts_max ? ts_max : (ts < ts_min ? ts_min : ts);
 }

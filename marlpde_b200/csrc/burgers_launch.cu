@@ -5,15 +5,16 @@ namespace mpde {
 
 template <typename T>
 static int launch_burgers_32(const SpectralParams<T>& p, cudaStream_t st) {
-    switch (pick_team(p.team_lanes, 32, 16, 4)) {
+    switch (pick_team(p.team_lanes, p.B, 32, p.flags, 16, 4)) {
         case 16: return launch_burgers_32_16<T>(p, st);
         case 8: return launch_burgers_32_8<T>(p, st);
+        case -8: return launch_burgers_32_8x<T>(p, st);
         default: return launch_burgers_32_4<T>(p, st);
     }
 }
 template <typename T>
 static int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st) {
-    switch (pick_team(p.team_lanes, 64, 32, 8)) {
+    switch (pick_team(p.team_lanes, p.B, 64, p.flags, 32, 8)) {
         case 32: return launch_burgers_64_32<T>(p, st);
         case 16: return launch_burgers_64_16<T>(p, st);
         default: return launch_burgers_64_8<T>(p, st);

@@ -653,16 +653,20 @@ struct BurgersWarp {
         if (spec_reward) {
             // burger_environment.py:172-176 on the running float32 sums
             const int A = prm.A;
-            T part = T(0);
+            // squared relative errors go back into the stash (over the reference row) and are summed in WAVENUMBER order
+            // by every lane: the same sequence of additions whatever the team size (variants must agree bitwise)
 #pragma unroll
             for (int p = 0; p < P; ++p)
                 if (kk[p] >= 1) {
                     const T es = (T)((double)acc32[p] / (double)(iout + 1));
                     const T er = stash[5 + kk[p]];
                     const T q = fabs(er - es) / er;
-                    part += q * q;
+                    stash[5 + kk[p]] = q * q;
                 }
-            part = team_sum(f, part) / T(H - 1);
+            __syncwarp(f.c.tmask);
+            T part = T(0);
+            for (int k = 1; k < H; ++k) part += stash[5 + k];
+            part = part / T(H - 1);
             const T r = live ? stash[4] - part : -inf;
             if (has) {
                 for (int a = tl; a < A; a += TS) {

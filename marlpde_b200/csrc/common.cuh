@@ -11,12 +11,15 @@ template <typename T> struct Cx { T re, im; };
 template <typename T> __device__ __forceinline__ Cx<T> cx(T re, T im) { Cx<T> r; r.re = re; r.im = im; return r; }
 template <typename T> __device__ __forceinline__ Cx<T> operator+(Cx<T> a, Cx<T> b) { return cx<T>(a.re + b.re, a.im + b.im); }
 template <typename T> __device__ __forceinline__ Cx<T> operator-(Cx<T> a, Cx<T> b) { return cx<T>(a.re - b.re, a.im - b.im); }
+// The library is compiled with -fmad=false: the compiler never fuses a multiply into an add on its own, so the same
+// source expression rounds identically in every template instantiation (the team-size variants must agree bitwise).
+// Fused multiply-adds are written out where they are wanted.
 template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
-    return cx<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+    return cx<T>(fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re));
 }
 // a * conj(b)
 template <typename T> __device__ __forceinline__ Cx<T> cmulc(Cx<T> a, Cx<T> b) {
-    return cx<T>(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im);
+    return cx<T>(fma(a.re, b.re, a.im * b.im), fma(a.im, b.re, -(a.re * b.im)));
 }
 template <typename T> __device__ __forceinline__ Cx<T> conj(Cx<T> a) { return cx<T>(a.re, -a.im); }
 

@@ -13,6 +13,7 @@ namespace mpde {
 template <typename T> int launch_burgers(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_32_16(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_32_8(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T> int launch_burgers_32_8x(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_32_4(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_64_32(const SpectralParams<T>& p, cudaStream_t st);
 template <typename T> int launch_burgers_64_16(const SpectralParams<T>& p, cudaStream_t st);

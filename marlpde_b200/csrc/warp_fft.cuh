@@ -266,7 +266,139 @@ struct WarpFFT<T, 16, 4, TWS> {
     }
 };
 
-template <typename T, int N, int TS_ = (N / 2 < 32 ? N / 2 : 32)>
+// 16 points on 8 lanes x 2 registers with EXACTLY the arithmetic of the 4 x 4 transform above (a radix-2^2
+// factorisation: the same two radix-4 passes, their butterflies spread over one in-register and three shuffle
+// stages, the same single twiddle W16^(t c) between the passes).  Every add, subtract and multiply has the same
+// operands in the same order, so both variants produce bit-identical spectra and fields -- which is what lets the
+// host choose the team size from the batch size without changing any result.
+// Layout: point j = 8 p + tl in register p (as the generic transform); wavenumber k = c + 4 d with
+// c = 2 (tl >> 2) + q in register q, d = bitrev2(tl & 3).
+// Selected with the team-size tag -8 (the plain 8 keeps the faster radix-2 shuffle network above, whose rounding differs).
+template <typename T, int TWS>
+struct WarpFFT<T, 16, -8, TWS> {
+    static constexpr int H = 16, TS = 8, P = 2;
+    static constexpr int SMEM_CX = 0;
+    int tl, base;
+    unsigned tmask;
+    bool lo4, b1, b0;                   // tl < 4, bit 1 and bit 0 of tl
+    Cx<T> wa, wb;                       // W16^(t' c0), W16^(t' (c0 + 1)): t' = tl & 3, c0 = 2 (tl >> 2)
+    int part[2];
+
+    __device__ __forceinline__ static int brev2(int x) { return ((x & 1) << 1) | ((x >> 1) & 1); }
+    __device__ __forceinline__ static int kidx(int q, int t) { return 2 * (t >> 2) + q + 4 * brev2(t & 3); }
+
+    __device__ __forceinline__ static Cx<T> tw16(const Cx<T>* __restrict__ tw, int m) {      // W16^m, m <= 9
+        const Cx<T> w = ldcx(tw + (m & 7) * TWS);
+        return m >= 8 ? cx<T>(-w.re, -w.im) : w;
+    }
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw, Cx<T>* /*team_smem*/ = nullptr) {
+        const int lane = threadIdx.x & 31;
+        tl = lane & 7;
+        base = lane & ~7;
+        tmask = 0xffu << base;
+        lo4 = tl < 4;
+        b1 = (tl & 2) != 0;
+        b0 = (tl & 1) != 0;
+        const int tp = tl & 3, c0 = 2 * (tl >> 2);
+        wa = tw16(tw, tp * c0);
+        wb = tw16(tw, tp * (c0 + 1));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int kn = (16 - kidx(q, tl)) & 15, cn = kn & 3, dn = kn >> 2;     // (cn & 1) == q
+            part[q] = base + 4 * (cn >> 1) + brev2(dn);
+        }
+    }
+    // r <- (lower lane of the pair ? r + o : o - r), the pair being lanes that differ in the bit whose sign is sg
+    __device__ __forceinline__ static Cx<T> pm(T sg, Cx<T> r, Cx<T> o) { return cx<T>(fma(sg, r.re, o.re), fma(sg, r.im, o.im)); }
+    // a1 -/+ i a3: sg = +1 -> (a1.re + a3.im, a1.im - a3.re) = a1 - i a3;  sg = -1 -> a1 + i a3
+    __device__ __forceinline__ static Cx<T> rot(T sg, Cx<T> a1, Cx<T> a3) { return cx<T>(fma(sg, a3.im, a1.re), fma(-sg, a3.re, a1.im)); }
+
+    template <bool INV>
+    __device__ __forceinline__ void first_pass(Cx<T> (&z)[2]) const {
+        if constexpr (!INV) {
+            // pass 1 (points j, j+4, j+8, j+12 of column t'): in-register stage, then lanes t' <-> t' + 4
+            const Cx<T> s = z[0] + z[1], d = z[0] - z[1];
+            const Cx<T> os = shfl_xor(s, 4, tmask), od = shfl_xor(d, 4, tmask);
+            const T sg = lo4 ? T(1) : T(-1);
+            z[0] = pm(sg, s, os);                                       // y0 = a0 + a2 | y2 = a0 - a2
+            z[1] = rot(sg, lo4 ? d : od, lo4 ? od : d);                 // y1 = a1 - i a3 | y3 = a1 + i a3
+        } else {
+            // pass 1 of the inverse runs over d = bitrev2(t'): lanes t' <-> t' ^ 1, then t' <-> t' ^ 2
+            const T sg0 = b0 ? T(-1) : T(1), sg1 = b1 ? T(-1) : T(1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const Cx<T> o = shfl_xor(z[q], 1, tmask);
+                z[q] = pm(sg0, z[q], o);                                 // a0, a1 (d = 0, 2) | a2, a3 (d = 1, 3)
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const Cx<T> o = shfl_xor(z[q], 2, tmask);
+                const Cx<T> plain = pm(sg1, z[q], o);                    // B0 = a0 + a2 | B2 = a0 - a2
+                const Cx<T> turned = rot(-sg1, b1 ? o : z[q], b1 ? z[q] : o);   // B1 = a1 + i a3 | B3 = a1 - i a3
+                z[q] = b0 ? turned : plain;
+            }
+        }
+    }
+    template <bool INV>
+    __device__ __forceinline__ void twiddle(Cx<T> (&z)[2]) const {
+        const Cx<T> t0 = INV ? cmulc(z[0], wa) : cmul(z[0], wa);
+        z[0] = lo4 ? z[0] : t0;                                          // c = 0 is never multiplied
+        z[1] = INV ? cmulc(z[1], wb) : cmul(z[1], wb);
+    }
+    template <bool INV>
+    __device__ __forceinline__ void second_pass(Cx<T> (&z)[2]) const {
+        if constexpr (!INV) {
+            // pass 2 over t' (lanes): t' <-> t' ^ 2, then t' <-> t' ^ 1
+            const T sg1 = b1 ? T(-1) : T(1), sg0 = b0 ? T(-1) : T(1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const Cx<T> o = shfl_xor(z[q], 2, tmask);
+                z[q] = pm(sg1, z[q], o);                                 // a0, a2 | a1, a3
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const Cx<T> o = shfl_xor(z[q], 1, tmask);
+                const Cx<T> plain = pm(sg0, z[q], o);                    // y0 = a0 + a2 | y2 = a0 - a2
+                const Cx<T> turned = rot(sg0, b0 ? o : z[q], b0 ? z[q] : o);    // y1 = a1 - i a3 | y3 = a1 + i a3
+                z[q] = b1 ? turned : plain;
+            }
+        } else {
+            // pass 2 of the inverse over c = 2 (tl >> 2) + q: lanes t' <-> t' + 4, then the in-register stage
+            const T sg = lo4 ? T(1) : T(-1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const Cx<T> o = shfl_xor(z[q], 4, tmask);
+                z[q] = pm(sg, z[q], o);                                  // a0, a2 | a1, a3
+            }
+            // lo: x[p=0] = a0 + a2, x[p=2] = a0 - a2;  hi: x[p=1] = a1 + i a3, x[p=3] = a1 - i a3
+            const Cx<T> u = lo4 ? z[1] : cx<T>(-z[1].im, z[1].re);
+            const Cx<T> r0 = z[0];
+            z[0] = r0 + u;
+            z[1] = r0 - u;
+        }
+    }
+    __device__ __forceinline__ void fwd(Cx<T> (&z)[2]) const {
+        first_pass<false>(z);
+        twiddle<false>(z);
+        second_pass<false>(z);
+    }
+    __device__ __forceinline__ void fwd2(Cx<T> (&za)[2], Cx<T> (&zb)[2]) const {
+        first_pass<false>(za);
+        first_pass<false>(zb);
+        twiddle<false>(za);
+        twiddle<false>(zb);
+        second_pass<false>(za);
+        second_pass<false>(zb);
+    }
+    __device__ __forceinline__ void inv(Cx<T> (&z)[2]) const {
+        first_pass<true>(z);
+        twiddle<true>(z);
+        second_pass<true>(z);
+    }
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[2], int q) const { return shfl(z[q], part[q], tmask); }
+};
+
+template <typename T, int N, int TS_ = (N / 2 < 32 ? N / 2 : 32)>      // TS_ < 0: tag of an alternative transform with |TS_| lanes
 struct RealFFT {
     static constexpr int H = N / 2;
     using C = WarpFFT<T, H, TS_, 2>;

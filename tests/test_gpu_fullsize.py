@@ -22,7 +22,7 @@ def team(monkeypatch):
     return set_team
 
 
-@pytest.mark.parametrize("ts", [16, 8, 4])
+@pytest.mark.parametrize("ts", [16, 8, 4, -8])
 @pytest.mark.parametrize("case", ["eddy_forced", "direct", "dsm", "ssm_act"])
 def test_every_team_size_matches_the_reference(golden, team, ts, case):
     """Free-running 60 steps against the reference's golden trajectory with the team size forced (MPDE_TS):
@@ -98,6 +98,28 @@ def test_full_size_config5_marl_mse(team):
     assert rel(r1, expect.cpu().numpy()) < 1e-9
 
 
+@pytest.mark.parametrize("case", ["eddy_forced", "direct", "ssm_act"])
+def test_eight_and_four_lane_kernels_agree_bitwise(golden, team, case):
+    """The radix-2^2 8-lane kernel (team_lanes=-8) and the 4-lane 4 x 4 shared-memory-transpose kernel perform the same
+    arithmetic: identical bits in v, Fn_old, u, state and spectral reward, which is what lets team_lanes=-1 follow the
+    batch size without changing any result."""
+    team(None)
+    g = golden("burger_steps.npz")
+    V, A = g[f"{case}/v"], g[f"{case}/actions"]
+    B = 13
+    rows = np.arange(B) % len(V)
+    ref = np.abs(np.random.default_rng(0).normal(1, 0.1, (61, 16))) + 0.1
+    out = []
+    for lanes in (-8, 4):       # -8: the radix-2^2 8-lane network
+        env, M = make_env(case, g, B=B, history=False, team_lanes=lanes)
+        env.IC(v0=V[rows]); env.set_spectrum_reference(ref)
+        a = A[rows % len(A)] if M else None
+        res = [env.step_n(a, 7), env.step_n(a, 3)]
+        out.append((env.v.clone(), env.Fn_old.clone(), env.u.clone(), res[1][0].clone(), res[1][1].clone(), res[0][1].clone()))
+    for x, y in zip(*out):
+        assert torch.equal(x, y), case
+
+
 def test_team_lanes_option_equals_env_override(golden, team):
     """Burger(team_lanes=4) selects the 4-lane kernels for that handle only: same bits as MPDE_TS=4, and the default
     handle next to it keeps the default team."""
@@ -105,7 +127,7 @@ def test_team_lanes_option_equals_env_override(golden, team):
     V, A = g["eddy_forced/v"], g["eddy_forced/actions"]
     team(None)
     a, _ = make_env("eddy_forced", g, B=5, history=False, team_lanes=4)
-    d, _ = make_env("eddy_forced", g, B=5, history=False)
+    d, _ = make_env("eddy_forced", g, B=5, history=False, team_lanes=-1)      # consistent auto: -8 at this batch size
     team(4)
     b, _ = make_env("eddy_forced", g, B=5, history=False)
     for e in (a, b, d):
@@ -115,7 +137,30 @@ def test_team_lanes_option_equals_env_override(golden, team):
     a.step_n(A[:5], 9, want_reward=False)
     d.step_n(A[:5], 9, want_reward=False)
     assert torch.equal(a.v, b.v)
-    assert rel(a.v, d.v.cpu().numpy()) < 1e-12 and not torch.equal(a.v, d.v)
+    assert torch.equal(a.v, d.v)          # 4-lane and radix-2^2 8-lane kernels agree bitwise
+    plain, _ = make_env("eddy_forced", g, B=5, history=False)                   # default: radix-2 8-lane network
+    plain.IC(v0=V[:5]); plain.step_n(A[:5], 9, want_reward=False)
+    assert rel(plain.v, a.v.cpu().numpy()) < 1e-12
+
+
+def test_consistent_auto_team_is_batch_size_invariant(team):
+    """team_lanes=-1: 4-lane kernels for the big batch, radix-2^2 8-lane kernels for the small re-run -- same bits."""
+    team(None)
+    from marlpde_b200 import Burger
+    B, N = 6400, 32
+    rng = np.random.default_rng(2)
+    seeds = 42 + (np.arange(B) % 5)
+    kw = dict(L=TWO_PI, N=N, dt=1e-3, nu=0.02, tend=1, case="turbulence", forcing=True, dforce=False, history=False, team_lanes=-1)
+    ref = np.abs(rng.normal(1.0, 0.1, (1001, 16))) * 1e-3 + 1e-6
+    acts = rng.uniform(0.0, 0.02, (B, 32))
+    big = Burger(nenvs=B, seed=seeds, **kw)
+    big.setup_basis(32, "hat"); big.set_spectrum_reference(ref)
+    st, rw = big.step_n(acts, 10)
+    idx = [0, 3, 3199, 6399]
+    small = Burger(nenvs=len(idx), seed=seeds[idx], **kw)
+    small.setup_basis(32, "hat"); small.set_spectrum_reference(ref)
+    s2, r2 = small.step_n(acts[idx], 10)
+    assert torch.equal(s2, st[idx]) and torch.equal(r2, rw[idx]) and torch.equal(small.v, big.v[idx])
 
 
 def test_full_size_config3_ks(golden):
