@@ -265,8 +265,8 @@ def gpu_arm(args):
     rot = pool * (2 if fused else 1)        # steps per graph: both copies of the double-buffered gather when fused
     extra = 1 if fused and not args.no_wait else 0      # signal+wait kernel per step
 
-    def capture(chains):
-        """Graph of one rotation.  chains > 1: independent batches alternate between `chains` streams inside the graph, so
+    def capture(chains, nsteps=None):
+        """Graph of one rotation (or of the first `nsteps` steps of it).  chains > 1: independent batches alternate between `chains` streams inside the graph, so
         one batch's tail (and, multi-GPU, its gather stores draining over NVLink) overlaps the next batch's kernel; a single
         chain serialises them (each kernel waits, through programmatic dependent launch, for its COMPLETE predecessor)."""
         l_before = sum(e.launch_count for e in envs)
@@ -276,19 +276,20 @@ def gpu_arm(args):
             cap = torch.cuda.current_stream()
             for cs in cstreams:
                 cs.wait_stream(cap)
-            for i in range(rot):
+            nst = rot if nsteps is None else nsteps
+            for i in range(nst):
                 if chains > 1:
                     with torch.cuda.stream(cstreams[i % chains]):
                         one_step(i, join=False)
                 else:
-                    one_step(i, join=(i == rot - 1))
+                    one_step(i, join=(i == nst - 1))
             for cs in cstreams:
                 cap.wait_stream(cs)
             if chains > 1 and fused and not args.no_wait:
                 cap.wait_stream(side)
-        n_k = (sum(e.launch_count for e in envs) - l_before) + extra * rot
+        n_k = (sum(e.launch_count for e in envs) - l_before) + extra * nst
         for g in gathers:                   # the capture pass only recorded: no step was published
-            g.step -= rot // pool
+            g.step -= nst // pool
         torch.cuda.synchronize()
         return g_, n_k
 
@@ -300,6 +301,11 @@ def gpu_arm(args):
             one_step(i)
         sync()
         graph, per_graph = capture(chains)
+    # single GPU: the K % rot steps that do not fill a rotation get their own (shorter) graph instead of Python launches
+    tail_graph, tail_len, per_tail = None, 0, 0
+    if args.graph and not fused and K % rot:
+        tail_len = K % rot
+        tail_graph, per_tail = capture(1, tail_len)
 
     def run_steps(first, n):
         """n RL steps starting at rotation index `first` (a multiple of pool when the graph is used)."""
@@ -312,6 +318,10 @@ def gpu_arm(args):
             for g in gathers:
                 g.step += reps * (rot // pool)
             first += reps * rot
+            if tail_graph is not None and n == tail_len and first % pool == 0:
+                tail_graph.replay()
+                launched += per_tail
+                n = 0
         l0 = sum(e.launch_count for e in envs)
         for i in range(n):
             one_step(first + i)
