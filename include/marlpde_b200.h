@@ -154,6 +154,15 @@ int mpde_reset_handoff(mpde_env* env, const void* vsrc_dev, int64_t nsrc, int32_
 int mpde_reset_turbulence(mpde_env* env, const int64_t* seed_dev, const double* offset_dev, const double* x_dev,
                           const double* amp_dev, const uint8_t* mask_dev, void* stream);
 
+/* Ground truth for the MSE reward at scale: sample the tensor-product B-spline that
+ * setGroundTruth builds (Burger.py:322-323; FITPACK knots tx [ntx], ty [nty], coefficients c [(ntx-kx-1)*(nty-ky-1)],
+ * degrees kx, ky in 1..3 -- all DEVICE double arrays) at out[q, i, j] = S(xq[q, j], tq[i]) for nq shifted grids of N points
+ * and `rows` times: the [nq, rows, N] table mpde_set_truth consumes (dtype MPDE_F64 / MPDE_F32).  FITPACK bispev
+ * semantics (arguments clamped to the spline's domain).  Returns 0 / -1. */
+int mpde_eval_spline_table(const double* tx_dev, int32_t ntx, const double* ty_dev, int32_t nty, const double* c_dev, int32_t kx,
+                           int32_t ky, const double* xq_dev, int64_t nq, int32_t N, const double* tq_dev, int64_t rows, void* out_dev,
+                           int32_t dtype, void* stream);
+
 /* step(actions) x nsub + getState + reward (Burger.py:333-499, 604-675; KS.py:230-274, 369-383;
  * Diffusion.py:164-216; Advection.py:154-213; burger_environment.py:148-176).
  *   actions_dev : [B, M] real or NULL (step() without actions)

@@ -246,13 +246,17 @@ class Burger(SpectralEnv):
         if self.f_truth is None:
             raise RuntimeError("getMseReward needs setGroundTruth(...) or set_truth_table(...)")
         uniq, inv = np.unique(shift, return_inverse=True)
-        tabs = []
+        grids = []
         for sh in uniq:
             newx = self.x + sh
             newx[newx > self.L] -= self.L
             newx[newx < 0] += self.L
-            tabs.append(self.f_truth.rows(newx, self.tt))
-        self.set_truth_table(np.stack(tabs), env_map=inv.astype(np.int32) if len(uniq) > 1 else None)
+            grids.append(newx)
+        if len(uniq) > 8:       # many distinct shifts (noise > 0 at scale): sample the spline on the device
+            tabs = self.f_truth.rows_device(np.stack(grids), self.tt, self.device, self.dtype)
+        else:
+            tabs = np.stack([self.f_truth.rows(g, self.tt) for g in grids])
+        self.set_truth_table(tabs, env_map=inv.astype(np.int32) if len(uniq) > 1 else None)
         self._truth_shift = key
 
     def _upload_forcing(self):

@@ -141,6 +141,31 @@ class TruthInterpolant:
         out = self._spline()(xs, ts).T
         return out[0] if out.shape[0] == 1 else out
 
+    def rows_device(self, xq, ts, device, dtype):
+        """Truth tables on the GPU: xq [nq, N] (one shifted / wrapped grid per row), ts [rows] -> tensor [nq, rows, N].
+        The spline is fitted on the host (FITPACK, as the reference does); its knots and coefficients are uploaded once and
+        sampled by ``mpde_eval_spline_table`` -- the part whose cost grows with the number of distinct shifts."""
+        import ctypes as C
+        import torch
+        from . import _lib as LB
+        lib = LB.lib()
+        if getattr(self, "_tck_dev", None) is None or self._tck_dev[0] != str(device):
+            tx, ty, c = self._spline().tck
+            up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+            self._tck_dev = (str(device), up(tx), up(ty), up(c))
+        _, tx, ty, c = self._tck_dev
+        xq = np.atleast_2d(np.asarray(xq, dtype=np.float64))
+        xd = torch.as_tensor(np.ascontiguousarray(xq), device=device)
+        td = torch.as_tensor(np.ascontiguousarray(np.asarray(ts, dtype=np.float64)), device=device)
+        out = torch.empty((xq.shape[0], td.numel(), xq.shape[1]), device=device, dtype=dtype)
+        st = torch.cuda.current_stream(device).cuda_stream
+        rc = lib.mpde_eval_spline_table(tx.data_ptr(), tx.numel(), ty.data_ptr(), ty.numel(), c.data_ptr(), self.order, self.order,
+                                        xd.data_ptr(), xq.shape[0], xq.shape[1], td.data_ptr(), td.numel(), out.data_ptr(),
+                                        LB.F64 if dtype == torch.float64 else LB.F32, st)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: mpde_eval_spline_table failed")
+        return out
+
     def rows(self, xq, ts):
         """Truth at the (unsorted) points xq for every time in ts -> [len(ts), len(xq)]."""
         order = np.argsort(xq, kind='stable')

@@ -64,3 +64,43 @@ def test_turbulence_ic_on_device_matches_the_host_loop(N):
     dev.step_n(None, 5, want_state=False, want_reward=False)
     host.step_n(None, 5, want_state=False, want_reward=False)
     assert rel(dev.v, host.v.cpu().numpy()) < 1e-11
+
+
+def test_spline_table_on_device_matches_fitpack():
+    """mpde_eval_spline_table against SciPy's FITPACK evaluation of the same spline, cubic and linear, for
+    shifted + wrapped grids; then the MSE reward of a batch with 20 distinct offsets (device-sampled truth tables) against
+    the same batch fed host-sampled tables."""
+    from marlpde_b200 import Burger
+    from marlpde_b200.hostmath import TruthInterpolant
+    rng = np.random.default_rng(4)
+    L, Nd, rows, N = TWO_PI, 128, 41, 32
+    xd = np.linspace(0, L, Nd, endpoint=False)
+    tt = np.concatenate(([0.], np.cumsum(np.full(rows - 1, 1e-3))))
+    uu = 1.0 + np.sin(2 * xd[None, :] + 40 * tt[:, None]) + 0.05 * rng.normal(size=(rows, Nd))
+    x = np.linspace(0, L, N, endpoint=False)
+    shifts = rng.normal(0, 0.4, 20)
+    grids = []
+    for sh in shifts:
+        g = x + sh
+        g[g > L] -= L
+        g[g < 0] += L
+        grids.append(g)
+    grids = np.stack(grids)
+    for kind in ("cubic", "linear"):
+        f = TruthInterpolant(xd, tt, uu, kind=kind)
+        dev = f.rows_device(grids, tt, torch.device("cuda", 0), torch.float64).cpu().numpy()
+        host = np.stack([f.rows(g, tt) for g in grids])
+        assert np.max(np.abs(dev - host)) < 1e-12 * np.max(np.abs(host)), kind
+    B = 20
+    kw = dict(L=L, N=N, dt=1e-3, nu=0.02, nsteps=rows - 1, case="sinus", seed=3, nenvs=B, history=False, offset=shifts, numAgents=4)
+    a, b = Burger(**kw), Burger(**kw)
+    a.setGroundTruth(xd, tt, uu)
+    a._ensure_truth(shifts)                                   # > 8 distinct shifts: sampled on the device
+    f = TruthInterpolant(xd, tt, uu, kind="cubic")
+    b.set_truth_table(np.stack([f.rows(g, tt) for g in grids]), env_map=np.arange(B, dtype=np.int32))
+    for env in (a, b):
+        env.setup_basis(8, "hat")
+    acts = rng.uniform(-0.1, 0.1, (B, 8))
+    _, ra = a.step_n(acts, 5)
+    _, rb = b.step_n(acts, 5)
+    assert rel(ra, rb.cpu().numpy()) < 1e-10
