@@ -44,6 +44,9 @@ enum mpde_reward { MPDE_REWARD_NONE = 0, MPDE_REWARD_SPECTRAL = 1, MPDE_REWARD_M
 #define MPDE_SSM      (1 << 2) /* Burger(ssm=True): static Smagorinsky closure                   */
 #define MPDE_DSM      (1 << 3) /* Burger(dsm=True): dynamic Smagorinsky closure                  */
 #define MPDE_IMPLICIT (1 << 4) /* Diffusion(implicit=True): implicit-Euler FDstep                */
+#define MPDE_FD       (1 << 5) /* Burger_fd: explicit Euler + finite differences (Burger_fd.py:335-476);  */
+                               /* warp-resident kernels only (N <= 256), state versions 0 and 2, no dsm  */
+#define MPDE_SSMFORCE (1 << 6) /* Burger_fd(ssmforce=True): actions are Smagorinsky coefficients          */
 
 /* fields for mpde_get / mpde_set */
 enum mpde_field {

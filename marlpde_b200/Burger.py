@@ -86,6 +86,7 @@ class Burger(SpectralEnv):
         self._forcing_dirty = True
 
         flags = (L_DFORCE if dforce else 0) | (L_FORCING if forcing else 0) | (L_SSM if ssm else 0) | (L_DSM if dsm else 0)
+        flags |= self._extra_flags()
         self._create(nenvs=B, N=N, L_=self.L, dt=self.dt, M=0, num_agents=numAgents, version=version,
                      stepper=self.stepper, flags=flags, device=device, dtype=dtype, team_lanes=team_lanes)
         L_check(self._lib.mpde_set_nu(self._h, LB.as_dp(np.ascontiguousarray(self._nu)), B))
@@ -109,6 +110,9 @@ class Burger(SpectralEnv):
             self.IC(u0=u0)
         else:
             self.IC(v0=v0)
+
+    def _extra_flags(self):
+        return 0
 
     # ------------------------------------------------------------------ simple attributes
     @property

@@ -15,7 +15,7 @@ BURGERS, KS, DIFFUSION, ADVECTION = 0, 1, 2, 3
 F64, F32 = 0, 1
 RUNNING, TRUNCATED = 0, 1
 REWARD_NONE, REWARD_SPECTRAL, REWARD_MSE, REWARD_DIRECT = 0, 1, 2, 3
-DFORCE, FORCING, SSM, DSM, IMPLICIT = 1, 2, 4, 8, 16
+DFORCE, FORCING, SSM, DSM, IMPLICIT, FD, SSMFORCE = 1, 2, 4, 8, 16, 32, 64
 (FIELD_U, FIELD_V, FIELD_FN_OLD, FIELD_U_PREV, FIELD_EK_SUM, FIELD_IOUTNUM, FIELD_T, FIELD_KPREV,
  FIELD_STATUS, FIELD_K, FIELD_NU, FIELD_ALPHA) = range(12)
 OPT_KS_UUROW, OPT_NUM_AGENTS, OPT_NUM_ACTIONS = 1, 2, 3

@@ -214,7 +214,17 @@ struct BurgersWarp {
 
         // ---- U = N * Re ifft(v) ---------------------------------------------------------------
         Cx<T> U[P], Uprev[P];
-        f.inv(v, vN.re, U);
+        // Burger_fd (generic kernel only): u is the primary variable and lives in the uprev slot; v = fft(u) is derived
+        const bool fd = SF < 0 && (flags & F_FD);
+        if (fd) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const Cx<T> t = ldcx(reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N) + p * TS + tl);
+                U[p] = cx<T>(t.re * T(N), t.im * T(N));          // exact: N is a power of two
+            }
+        } else {
+            f.inv(v, vN.re, U);
+        }
 #pragma unroll
         for (int p = 0; p < P; ++p) Uprev[p] = U[p];
         const bool v1 = !LEAN && prm.version == 1;             // state version 1 needs u of the previous step (dudt)
@@ -300,6 +310,65 @@ struct BurgersWarp {
         const bool multi_col = !LEAN && prm.stepper > 1;
         const bool eddy = (flags & F_ACTIONS) && !(flags & F_DFORCE);
         for (int it = 0; it < nsub; ++it) {
+          if (fd) {
+            // ---- Burger_fd.step (Burger_fd.py:335-476): u += dt (nu u_xx - u u_x + forcing), v = fft(u) ----------------
+            T left[P], right[P];
+            halo(f, U, left, right);
+            const T delta = T(2.0 * 3.14159265358979323846 / N);
+            Cx<T> c3[3];                       // spectrum of the stochastic forcing at k = 1, 2, 3 (this step's column)
+            if (flags & F_FORCING) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c3[k] = ldcx(fc_row + col * 3 + k);
+                col = (col + 1 == prm.stepper) ? 0 : col + 1;
+            }
+            Cx<T> zz[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (it == nsub - 1) Uprev[p] = U[p];
+                const T ue = U[p].re * invN, uo = U[p].im * invN, ul = left[p] * invN, ur = right[p] * invN;
+                const T dudx[2] = {(ue - ul) * inv_dx, (uo - ue) * inv_dx};                                   // :465
+                const T d2[2] = {(uo - T(2) * ue + ul) * inv_dx2, (ur - T(2) * uo + ue) * inv_dx2};            // :466
+                const T uu2[2] = {ue, uo};
+                const T act[2] = {(flags & F_DFORCE) ? fa[p].re : fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
+                                  (flags & F_DFORCE) ? fa[p].im : fa[p].im * (U[p].re - T(2) * U[p].im + right[p])};
+                T un[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    T forc = T(0);
+                    if (flags & F_SSM) forc = (T(0.1) * delta) * (T(0.1) * delta) * fabs(dudx[h]) * d2[h];             // :343-355
+                    if (flags & F_FORCING) {           // f_j = (2/N) Re sum_k c_k exp(2 pi i k j / N)  (:406-417, replaces)
+                        const int j = 2 * (p * TS + tl) + h;
+                        forc = T(0);
+#pragma unroll
+                        for (int k = 1; k <= 3; ++k) {
+                            const int m = (k * j) & (N - 1);
+                            const Cx<T> w = ldcx(prm.tw + (m & (N / 2 - 1)));          // exp(-2 pi i m / N), m < N/2
+                            const T sg = m >= N / 2 ? T(-1) : T(1);
+                            forc += (T(2) * invN) * sg * (c3[k - 1].re * w.re + c3[k - 1].im * w.im);
+                        }
+                    }
+                    if (flags & F_ACTIONS) {
+                        T af = act[h];
+                        if (flags & F_SSMFORCE) af = (af * delta) * (af * delta) * fabs(dudx[h]) * d2[h];               // :447-455
+                        forc += af;
+                    }
+                    un[h] = uu2[h] + dt * (nu * d2[h] - uu2[h] * dudx[h] + forc);                                       // :468
+                }
+                U[p] = cx<T>(un[0] * T(N), un[1] * T(N));
+                zz[p] = U[p];
+            }
+            Cx<T> X[P];
+            T XN;
+            f.fwd(zz, X, XN, T(1), ws1);                                                                        // :469
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                v[p] = cx<T>(X[p].re * invN, X[p].im * invN);
+                bad |= blown(v[p]);
+            }
+            vN = cx<T>(XN * invN, T(0));
+            if (f.dc) bad |= blown(vN);
+            iout += 1;
+          } else {
             // nonlinear term X = fft(u^2 / 2) (Burger.py:487); with eddy-viscosity actions the forcing
             // (a @ basis) * d2u/dx2 (Burger.py:445-450) is transformed in the same pass
             Cx<T> z[P], X[P], S[P];
@@ -464,6 +533,7 @@ struct BurgersWarp {
 
             // U = N Re ifft(v) (Burger.py:491)
             f.inv(v, vN.re, U);
+          }
 
             // float32 spectrum chain (Q6): Ek row from complex64(v), sequential float32 sum
 #pragma unroll
@@ -524,7 +594,9 @@ struct BurgersWarp {
                 stcx(prm.v + e * NH + kk[p], v[p]);
                 stcx(prm.fn + e * NH + kk[p], fn[p]);
                 prm.acc[e * NH + kk[p]] = acc32[p];
-                if (v1)                    // u before the last sub-step: only state version 1 (dudt) reads it
+                if (fd)                    // Burger_fd: the field itself is the primary variable
+                    stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(U[p].re * invN, U[p].im * invN));
+                else if (v1)               // u before the last sub-step: only state version 1 (dudt) reads it
                     stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
             }
             if (f.dc) {

@@ -364,6 +364,8 @@ struct Env : mpde_env {
         if (cfg.flags & MPDE_FORCING) flags |= F_FORCING;
         if (cfg.flags & MPDE_SSM) flags |= F_SSM;
         if (cfg.flags & MPDE_DSM) flags |= F_DSM;
+        if (cfg.flags & MPDE_FD) flags |= F_FD;
+        if (cfg.flags & MPDE_SSMFORCE) flags |= F_SSMFORCE;
         p.A = cfg.num_agents;
         p.M = cfg.M;
         if (actions) {
@@ -592,6 +594,12 @@ int mpde_create(const mpde_config* cfg, mpde_env** out) {
     if (cfg->num_agents < 1 || cfg->N % cfg->num_agents) return fail("create: num_agents must divide N");
     if (cfg->stepper < 1) return fail("create: stepper must be >= 1");
     if ((cfg->flags & MPDE_SSM) && (cfg->flags & MPDE_DSM)) return fail("create: ssm and dsm are exclusive (Burger.py:50)");
+    if (cfg->flags & MPDE_FD) {
+        if (cfg->equation != MPDE_BURGERS) return fail("create: MPDE_FD is a Burgers option (Burger_fd)");
+        if (cfg->N > 256) return fail("create: Burger_fd is available for N <= 256");
+        if (cfg->flags & MPDE_DSM) return fail("create: Burger_fd with the dynamic Smagorinsky closure is not supported");
+        if (cfg->version == 1 || cfg->version > 2) return fail("create: Burger_fd supports state versions 0 and 2");
+    }
     if (cfg->version < 0 || cfg->version > 4) return fail("create: version must be 0..4");
     if (!(cfg->L > 0) || !(cfg->dt > 0)) return fail("create: L and dt must be positive");
     int ndev = 0;

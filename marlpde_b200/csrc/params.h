@@ -14,6 +14,9 @@ enum : int {
     F_BASIS_DENSE = 1 << 5,   // basis has >2 non-zeros in some column: use the dense [M,N] table
     F_FORCING_PER_ENV = 1 << 6,
     F_NO_ADVANCE = 1 << 7,    // nsub == 0: only evaluate the state (getState without stepping)
+    // 1 << 8: F_KS_UUROW (ks_warp.cuh)
+    F_FD = 1 << 9,            // Burger_fd: explicit Euler + finite differences in real space (Burger_fd.py:335-476)
+    F_SSMFORCE = 1 << 10,     // Burger_fd(ssmforce=True): the action is a Smagorinsky coefficient (Burger_fd.py:447-455)
 };
 
 enum : int { REWARD_NONE = 0, REWARD_SPECTRAL = 1, REWARD_MSE = 2, REWARD_DIRECT = 3 };
