@@ -231,6 +231,10 @@ const char* mpde_peer_last_error(void);
  * so step + signal + wait replay from a CUDA graph; neither needs to sit on the step kernels' own stream. */
 int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs, void* const* reward_ptrs, int64_t parity_stride,
                          void* mc_state, void* mc_reward);
+/* this rank's OWN slab (copy 0) inside its gather buffer: lets mpde_step_host / mpde_step_host_packed run with the gather
+ * bound (the kernel writes the rows there -- through the multicast address when one is bound -- and the D2H copy reads
+ * the copy of the current parity).  local_reward = local_state + B*S for the packed single-copy path. */
+int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward);
 int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream);
 int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
 /* signal_next + wait_next as ONE kernel launch */

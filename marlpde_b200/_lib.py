@@ -67,6 +67,7 @@ SIGNATURES = {
     "mpde_peer_wait": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp]),
     "mpde_peer_last_error": (C.c_char_p, []),
     "mpde_set_peer_output": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp]),
+    "mpde_set_peer_local": (C.c_int, [_vp, _vp, _vp]),
     "mpde_peer_signal_next": (C.c_int, [C.POINTER(_vp), _i32, _vp, _vp]),
     "mpde_peer_exchange_next": (C.c_int, [C.POINTER(_vp), _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "mpde_peer_wait_next": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp]),

@@ -56,6 +56,7 @@ struct mpde_env {
     virtual int step_host_packed(const void* actions, int nsub, void* out, cudaStream_t st) = 0;
     virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
                                 void* mc_reward) = 0;
+    virtual int set_peer_local(void* state, void* reward) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -278,6 +279,7 @@ struct Env : mpde_env {
                         void* mc_reward) override {
         peer_bound = false;
         peer_steps = 0;
+        peer_local_state = peer_local_reward = nullptr;
         prm.peer = PeerSink{};
         if (n_data == 0 && parity_stride == 0 && !mc_state && !mc_reward) return 0;
         if (cfg.equation != MPDE_BURGERS || cfg.N > 256)
@@ -299,6 +301,13 @@ struct Env : mpde_env {
         ps.mc_reward = mc_reward;
         prm.peer = ps;
         peer_bound = true;
+        return 0;
+    }
+    // this rank's own slab (copy 0) of the gather buffers: where mpde_step_host finds the rows it copies to the host
+    T *peer_local_state = nullptr, *peer_local_reward = nullptr;
+    int set_peer_local(void* state, void* reward) override {
+        peer_local_state = static_cast<T*>(state);
+        peer_local_reward = static_cast<T*>(reward);
         return 0;
     }
     bool peer_bound = false;
@@ -421,27 +430,31 @@ struct Env : mpde_env {
     // graph and replayed by later calls: one driver call per RL step instead of four (MPDE_HOST_GRAPH=0 disables;
     // a stream that is already being captured by the caller, or the legacy default stream, gets the plain chain).
     struct HostGraph {
-        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec; bool packed;
+        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec; bool packed; int parity;
     };
     std::vector<HostGraph> host_graphs;
     int step_host_enqueue(const void* actions, int nsub, void* state_out, void* reward_out, size_t na, size_t ns, size_t nr,
                           cudaStream_t st) {
-        T* const stage_state = stage_out;
-        T* const stage_reward = stage_out + ns;
+        // with a fused gather bound the kernel writes this rank's rows into its slab of the gather buffer (copy = parity
+        // of the step about to be enqueued); the host copy reads them from there
+        T* const stage_state = peer_bound ? peer_local_state : stage_out;
+        T* const stage_reward = peer_bound ? peer_local_reward : stage_out + ns;
+        const int64_t poff = peer_bound ? (peer_steps & 1) * prm.peer.parity_stride : 0;
         if (na) CU(cudaMemcpyAsync(stage_act, actions, na * sizeof(T), cudaMemcpyHostToDevice, st));
         if (step(na ? stage_act : nullptr, nsub, ns ? stage_state : nullptr, nr ? stage_reward : nullptr, st)) return -1;
-        if (ns && nr && packed_out && reward_out == static_cast<T*>(state_out) + ns) {
-            CU(cudaMemcpyAsync(state_out, stage_state, (ns + nr) * sizeof(T), cudaMemcpyDeviceToHost, st));
+        if (ns && nr && packed_out && reward_out == static_cast<T*>(state_out) + ns && stage_reward == stage_state + ns) {
+            CU(cudaMemcpyAsync(state_out, stage_state + poff, (ns + nr) * sizeof(T), cudaMemcpyDeviceToHost, st));
             return 0;
         }
-        if (ns) CU(cudaMemcpyAsync(state_out, stage_state, ns * sizeof(T), cudaMemcpyDeviceToHost, st));
-        if (nr) CU(cudaMemcpyAsync(reward_out, stage_reward, nr * sizeof(T), cudaMemcpyDeviceToHost, st));
+        if (ns) CU(cudaMemcpyAsync(state_out, stage_state + poff, ns * sizeof(T), cudaMemcpyDeviceToHost, st));
+        if (nr) CU(cudaMemcpyAsync(reward_out, stage_reward + poff, nr * sizeof(T), cudaMemcpyDeviceToHost, st));
         return 0;
     }
     int step_host(const void* actions, int nsub, void* state_out, void* reward_out, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
-        if (peer_bound)
-            return fail("step_host: a fused peer gather is bound; step with device buffers (mpde_step) and copy the rows out");
+        if (peer_bound && (!peer_local_state || !peer_local_reward))
+            return fail("step_host: a fused peer gather is bound; name this rank's own slab with mpde_set_peer_local first");
+        const int parity = peer_bound ? (int)(peer_steps & 1) : 0;
         const size_t B = (size_t)cfg.nenvs;
         const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
         const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
@@ -454,8 +467,9 @@ struct Env : mpde_env {
             return step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
         for (const HostGraph& g : host_graphs)
             if (g.actions == actions && g.state == state_out && g.reward == reward_out && g.nsub == nsub && g.epoch == epoch &&
-                g.packed == packed_out) {
+                g.packed == packed_out && g.parity == parity) {
                 CU(cudaGraphLaunch(g.exec, st));
+                if (peer_bound) ++peer_steps;
                 launches += g.kernels;
                 return 0;
             }
@@ -476,11 +490,11 @@ struct Env : mpde_env {
         const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) return fail(std::string("step_host: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
-        if (host_graphs.size() >= 4) {
+        if (host_graphs.size() >= 8) {
             cudaGraphExecDestroy(host_graphs.front().exec);
             host_graphs.erase(host_graphs.begin());
         }
-        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec, packed_out});
+        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec, packed_out, parity});
         CU(cudaGraphLaunch(exec, st));
         launches += kernels;
         return 0;
@@ -686,6 +700,10 @@ int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs,
                          void* mc_state, void* mc_reward) {
     if (env) ++env->epoch;
     return env ? env->set_peer_output(n_data, state_ptrs, reward_ptrs, parity_stride, mc_state, mc_reward) : fail("null argument");
+}
+int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward) {
+    if (env) ++env->epoch;
+    return env ? env->set_peer_local(local_state, local_reward) : fail("null argument");
 }
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");

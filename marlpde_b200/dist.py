@@ -203,6 +203,11 @@ class PeerGather:
         rc = self._lib.mpde_set_peer_output(env._h, len(others), st, rw, stride, mc_state, mc_reward)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
+        base = self._base + slab            # this rank's own slab, copy 0: lets step_n_host run with the gather bound
+        rc = self._lib.mpde_set_peer_local(env._h, base, base + n_local * S * self._item)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
+        env._peer_host_ok = True
         self._fused = env
         env._state_at = env._reward_at = -1
 

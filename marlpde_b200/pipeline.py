@@ -33,12 +33,15 @@ class HostPipeline:
         """Start one RL step of batch k with the host-side ``actions`` ([B,M]; None = reuse the pinned buffer)."""
         if actions_host is not None:
             self.act_host[k].copy_(torch.as_tensor(actions_host))
-        if self.post_step is None and hasattr(self.envs[k], "step_n_host"):
-            # one library call enqueues H2D -> kernel -> D2H on this slot's stream
-            env = self.envs[k]
+        env = self.envs[k]
+        if hasattr(env, "step_n_host") and (self.post_step is None or getattr(env, "_peer_host_ok", False)):
+            # one library call enqueues H2D -> kernel -> D2H on this slot's stream (a cached CUDA graph)
             packed = self.out_host[k] if (env._spec_ref is not None or env._truth_shift is not None) else None
             env.step_n_host(self.act_host[k], self.n_sub, self.state_host[k], self.reward_host[k], stream=self.streams[k],
                             packed_out=packed)
+            if self.post_step is not None:      # fused multi-GPU gather: publish / wait behind the step on the same stream
+                with torch.cuda.stream(self.streams[k]):
+                    self.post_step(k, None, None)
             self.done[k].record(self.streams[k])
         else:
             with torch.cuda.stream(self.streams[k]):

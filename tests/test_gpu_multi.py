@@ -176,3 +176,33 @@ def test_two_gpu_marl_mse_fused_gather_bitwise():
     for o in outs:
         assert o[1].shape == (B, 3 * N) and o[2].shape == (B, N)
         assert np.array_equal(o[1], st.cpu().numpy()) and np.array_equal(o[2], rw.cpu().numpy())
+
+
+def test_host_pipeline_with_fused_gather_single_rank():
+    """mpde_step_host with a fused gather bound (mpde_set_peer_local): the kernel writes this rank's rows into its slab of the
+    (double-buffered) gather buffer and the packed D2H copy reads them from there -- same bits as the plain device step, and the
+    gathered copy holds the same rows."""
+    from marlpde_b200 import dist as mdist
+    from marlpde_b200.pipeline import HostPipeline
+    torch.cuda.set_device(0)
+    sb = mdist.ShardedBatch(B, _factory, transport="fused")
+    ref = _factory(B, np.arange(B))
+
+    def post(k, st, rw):
+        sb._peer.step += 1
+        sb._peer.exchange_next()
+
+    pipe = HostPipeline([sb.env], 10, post_step=post)
+    a = _acts()
+    a_dev = a.cuda()
+    for k in range(5):
+        pipe.submit(0, a)
+        st_h, rw_h = pipe.collect(0)
+        st, rw = ref.step_n(a_dev, 10)
+        torch.cuda.synchronize()
+        sb._peer.check()
+        assert torch.equal(st_h, st.cpu()) and torch.equal(rw_h, rw.cpu()), k
+        S = st.shape[1]
+        cur = sb._peer.current()[0]
+        assert torch.equal(cur[:B * S].view(B, S), st) and torch.equal(cur[B * S:].view(B, 1), rw), k
+    sb._peer.close()
