@@ -4,11 +4,14 @@ env-steps/s, batched Burgers LES N=32 x 4096 envs per GPU, fp64, stochastic forc
 spectral reward, nIntermediate = 10 solver steps per RL step).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA)
-  python bench.py --impl reference ...                             # CPU reference arm (numpy port)
+  python bench.py --impl reference ...                             # CPU arm: the reference's own Burger class
 
-One "step" = one RL step of the whole batch = ONE kernel launch: 10 ABCN solver steps with
-the actions held fixed + getState + spectral reward (burger_environment.py:148-176).
-Prints ONE JSON line (see the driver contract in the task description).
+One "step" = one RL step of one batch = ONE kernel launch: 10 ABCN solver steps with the actions held
+fixed + getState + spectral reward (burger_environment.py:148-176).  Prints ONE JSON line (driver contract).
+
+Timed region: the K steps are captured once into ONE CUDA graph (pool of independent batches in rotation, so the
+working set exceeds L2) and replayed; multi-GPU runs use the same graph with the gather fused into the step
+kernel (mpde_step_fused) -- whatever K the driver asks for, no step is launched from Python.
 """
 import argparse
 import json
@@ -34,20 +37,29 @@ STABLE_SEEDS = (50, 59, 81, 89)
 # trip; with NSUB fused sub-steps the state makes that round trip once per launch, so bytes per env-step = 1912 / NSUB):
 #   read  actions M*8 + v,Fn_old 2*(N+2)*8 + forcing coefficients 6*8 + Ek sums (N/2)*8
 #   write v,Fn_old 2*(N+2)*8 + Ek sums (N/2)*8 + state S*8 + reward A*8          = 8*(32+136+6+32+32+1) = 1912 B
-# (the kernel's own layout moves a little less: float32 Ek sums, no u_prev row for state version 0 -> 1844 B)
 BYTES_PER_ENV_LAUNCH = 8 * (M + 4 * (N + 2) + 6 + N + N + 1)
 FLOPS_PER_ENV_STEP = 2600           # algorithmic fp64 flops of one Burgers N=32 solver step
-FP64_PEAK_TFLOPS = 33.2             # measured on this pool's B200 with tools/microbench.cu (profiles/r1_microbench_b200.md)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary_final.md): the reads
-# are the cold-cache state + actions; the 3.6 MB of results are still dirty in the 126 MB L2 when the replay ends
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 3.951e6
+BYTES_C5 = 8 * (M + 4 * (N + 2) + 3 * N + N)                  # 2368 B per env per launch
+BYTES_KS = 8 * (64 + 2 * (64 + 2) + 64 + 128 + 1)             # 3112 B per env per launch
+FLOPS_KS_STEP, FLOPS_DNS_STEP = 15000, 82000
+REF_DIR = os.path.join(ROOT, "baseline", "_ref", "_model")     # tools/install_ref.sh (git-ignored, travels with gpurun)
+
+
+def kernel_facts():
+    """Machine / profile facts measured by the tools (not constants of this file): profiles/kernel_facts.json is written
+    by tools/ncu_summary.py (ncu --set full DRAM bytes per launch) and tools/microbench.cu (FP64 DFMA peak)."""
+    p = os.path.join(ROOT, "profiles", "kernel_facts.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -89,117 +101,197 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def spectrum_table(seed=0):
+    """Synthetic stand-in for dns.Ek_ktt[:, :N/2] (5001 rows): same shape / indexing as burger_environment.py:174."""
+    return np.abs(np.random.default_rng(seed).normal(1.0, 0.1, (int(TEND / DT) + 1, N // 2))) * 1e-3 + 1e-6
+
+
 # ----------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    """One process = one reference-style environment stepped one solver step per Python call
-    (the reference has no batching: burger_environment.py:134-192)."""
-    seed, seconds, rl_steps = args
+def _cpu_worker_reference(args):
+    """One process = ONE environment of the UNMODIFIED reference class (baseline/_ref/_model/Burger.py), driven the way
+    burger_environment.environment drives it in spectral-reward mode (burger_environment.py:134-192): nIntermediate x
+    sgs.step(actions), sgs.getState(), sgs.compute_Ek() (rescans the whole history, as the reference does), kRelErr,
+    reward; a FloatingPointError (np.seterr raise, Burger.py:8) or the end of the episode starts a new episode with a
+    new Burger object, as Korali would."""
+    idx, seconds = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, REF_DIR)
+    import Burger as RB
+    rng = np.random.default_rng(idx)
+    ref = spectrum_table()
+    gs = N
+
+    def new_env(ep):
+        sgs = RB.Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=True, dforce=False,
+                        seed=42 + idx + 1000 * ep, version=0, noise=0., s=1)
+        sgs.setup_basis(M, "hat")
+        return sgs
+
+    actions = rng.uniform(0.02, 0.1, M).tolist()
+    episodes, rl_done, prev = 0, 0, 0.
+    sgs = new_env(0)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        try:
+            for _ in range(NSUB):
+                sgs.step(actions)
+            state = sgs.getState()                                                            # noqa: F841
+            sgs.compute_Ek()
+            k = np.mean(((np.abs(ref[sgs.ioutnum, 1:gs // 2] - sgs.Ek_ktt[sgs.ioutnum, 1:gs // 2])) / ref[sgs.ioutnum, 1:gs // 2]) ** 2)
+            reward = prev - k                                                                 # noqa: F841
+            prev = k
+            rl_done += 1
+            if sgs.ioutnum + NSUB > sgs.nsteps:
+                raise FloatingPointError("episode over")
+        except FloatingPointError:
+            episodes += 1
+            prev = 0.
+            sgs = new_env(episodes)
+    return rl_done * NSUB, time.perf_counter() - t0, episodes
+
+
+def _cpu_worker_port(args):
+    """Fallback when baseline/_ref is absent: the repo's numpy restatement (oracle/), one environment per process,
+    one step() per Python call.  Environments are re-initialised before they blow up (alive check every RL step)."""
+    idx, seconds = args
     os.environ["OMP_NUM_THREADS"] = "1"
     from oracle.burger_oracle import BurgerOracle, forcing_tables, turbulence_ic
     from oracle.common import grid, spectral_rel_err
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(idx)
     o = BurgerOracle(B=1, L=L_DOM, N=N, dt=DT, nu=NU, forcing=True, dforce=False)
     o.setup_basis(M, "hat")
-    sd = STABLE_SEEDS[seed % len(STABLE_SEEDS)]
+    sd = STABLE_SEEDS[idx % len(STABLE_SEEDS)]
     r1, r2 = forcing_tables(sd, int(TEND / DT))
     o.set_forcing_tables(r1[:, :1], r2[:, :1])
-    o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, sd)[None])
-    ref = np.abs(rng.normal(1.0, 0.1, (5001, N // 2))) * 1e-3 + 1e-6
-    acts = np.full((1, M), rng.uniform(0.05, 0.1))
-    prev, done, t0 = 0.0, 0, time.perf_counter()
-    while True:
+    u0 = turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, sd)[None]
+    o.IC(u0=u0)
+    ref = spectrum_table()
+    acts = rng.uniform(0.02, 0.1, (1, M))
+    done, episodes, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
         for _ in range(NSUB):
             o.step(acts)
         o.state()
-        err = spectral_rel_err(ref[min(o.ioutnum, 5000)], o.Ek_ktt_row()[0], N)
-        prev = err
+        spectral_rel_err(ref[min(o.ioutnum, 5000)], o.Ek_ktt_row()[0], N)
         done += 1
-        if o.ioutnum >= 4000:
-            o.IC(u0=turbulence_ic(grid(L_DOM, N), L_DOM, N, 0.0, sd)[None])
-        if (rl_steps and done >= rl_steps) or (not rl_steps and time.perf_counter() - t0 >= seconds):
-            break
-    return done * NSUB, time.perf_counter() - t0
+        if o.ioutnum >= 3000 or not np.all(np.abs(o.u) < 1e3):          # new episode before anything overflows
+            o.IC(u0=u0)
+            episodes += 1
+    return done * NSUB, time.perf_counter() - t0, episodes
 
 
-def cpu_run(seconds=None, rl_steps=None, cores=None):
+def cpu_run(seconds, cores=None):
     cores = cores or len(os.sched_getaffinity(0))
+    kind = "reference" if os.path.exists(os.path.join(REF_DIR, "Burger.py")) else "port"
+    worker = _cpu_worker_reference if kind == "reference" else _cpu_worker_port
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(i, seconds, rl_steps) for i in range(cores)])
-        wall = time.perf_counter() - t0
+        res = pool.map(worker, [(i, seconds) for i in range(cores)])
     steps = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return steps / busy, cores, steps, wall
+    what = ("the UNMODIFIED reference Burger class (baseline/_ref/_model, tools/install_ref.sh) driven as burger_environment.py:134-192 "
+            "does: 10 x step(actions) + getState + compute_Ek (whole-history rescan) + spectral reward per RL step"
+            if kind == "reference" else
+            "the repo's numpy restatement (oracle/; baseline/_ref absent): 10 x step + state + spectral reward per RL step")
+    sample = (f"{cores} single-environment processes (one per host core, OMP_NUM_THREADS=1) x {seconds:.0f} s of the bench workload "
+              f"(Burgers N=32, forcing, eddy-viscosity actions, M=32 hat basis); {what}; "
+              f"{sum(r[2] for r in res)} episodes restarted")
+    return steps / busy, cores, kind, sample
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: every step = `cores` environments x 1 RL step (10 solver steps), all host cores busy
-    cores = len(os.sched_getaffinity(0))
-    total_rl = args.steps + args.warmup
-    per_proc = max(1, min(total_rl, 400))
-    value, cores, steps, wall = cpu_run(rl_steps=per_proc, cores=cores)
-    sample = (f"{cores} single-env numpy-port processes (one per host core) x {per_proc} RL steps x {NSUB} solver steps, "
-              "Burgers N=32 forcing+eddy action+spectral reward, one step() per Python call as in the reference")
+    seconds = float(min(60.0, max(4.0, args.cpu_seconds)))
+    value, cores, kind, sample = cpu_run(seconds)
     line = {
         "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores * NSUB / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "one step of this arm = one RL step (10 solver steps) of `cores` environments, one per host core; the sample is "
+                "time-boxed, --steps/--warmup only label the line",
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, transport=None):
-    what = (f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
-            f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
-            f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of the batch")
-    if WORKLOAD == "c5":
-        what = (f"MARL Burgers N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[4]), fp64, {N} per-gridpoint agents (state windows "
-                f"of 3, one eddy-viscosity action each), MSE reward vs a shared truth table, nIntermediate={NSUB}; 4-lane teams")
-    return {"workload": what,
+def workload_config(n_gpus):
+    # identical in both arms (the driver compares the config of the reference arm with ours)
+    return {"workload": (f"Burgers LES N={N} x {B_PER_GPU} envs/GPU (BASELINE configs[1]), fp64, M={M} hat basis, "
+                         f"eddy-viscosity actions (dforce=False), 3-mode stochastic forcing, spectral reward, "
+                         f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of one batch"),
             "envs_per_gpu": B_PER_GPU, "N": N, "M": M, "n_intermediate": NSUB, "global_envs": B_PER_GPU * n_gpus,
             "l2": f"rotating pool of {POOL} independent batches per GPU (state working set > 126 MB L2)",
-            "parallelism": (f"env-sharded x{n_gpus}, state+reward gathered to every rank per RL step by {transport or 'peer'} "
-                            "stores fused into the step kernel (NVLink / NVSwitch, no NCCL call)") if n_gpus > 1 else "single GPU"}
+            "parallelism": "single GPU" if n_gpus == 1 else f"env-sharded x{n_gpus}, state+reward rows gathered to every rank each RL step"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
-WORKLOAD = "c2"            # --workload c5 switches to BASELINE configs[4] per GPU (diagnostic; the bench line is c2)
+def make_batch(torch, device, seed0, B=None, team_lanes=0, spec=None):
+    """One batch of the bench workload (BASELINE configs[1])."""
+    from marlpde_b200 import Burger
+    B = B or B_PER_GPU
+    # forced N=32 LES blows up for most forcing seeds within ~10^3 steps (the reference's own physics);
+    # these four stay bounded for a whole episode under a positive eddy viscosity, so every
+    # environment stays alive (= does all its arithmetic) during the timed region
+    seeds = np.array(STABLE_SEEDS)[(np.arange(B) + seed0) % len(STABLE_SEEDS)]
+    env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=True, dforce=False, seed=seeds,
+                 nenvs=B, device=device, history=False, team_lanes=team_lanes)
+    env.setup_basis(M, "hat")
+    env.set_spectrum_reference(spectrum_table() if spec is None else spec)
+    return env
 
 
-def make_batch_c5(torch, device, seed0):
+def make_batch_c5(torch, device, seed0, B=8192):
     """BASELINE configs[4] per GPU: MARL Burgers N=32, 32 per-gridpoint agents (state windows of 3, one action each),
     MSE reward against a shared truth table, 4-lane teams (the large-batch kernel)."""
     from marlpde_b200 import Burger
-    seeds = np.array(STABLE_SEEDS)[(np.arange(B_PER_GPU) + seed0) % len(STABLE_SEEDS)]
+    seeds = np.array(STABLE_SEEDS)[(np.arange(B) + seed0) % len(STABLE_SEEDS)]
     env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=False, dforce=False, seed=seeds, version=0,
-                 numAgents=N, nenvs=B_PER_GPU, device=device, history=False, team_lanes=4)
+                 numAgents=N, nenvs=B, device=device, history=False, team_lanes=4)
     env.setup_basis(M, "hat")
     env.set_truth_table(np.random.default_rng(seed0).normal(1.0, 0.3, (int(TEND / DT) + 1, N))[None])
     return env
 
 
-def make_batch(torch, device, seed0):
-    if WORKLOAD == "c5":
-        return make_batch_c5(torch, device, seed0)
-    from marlpde_b200 import Burger
-    # forced N=32 LES blows up for most forcing seeds within ~10^3 steps (the reference's own physics);
-    # these four stay bounded for a whole episode under a positive eddy viscosity, so every
-    # environment stays alive (= does all its arithmetic) during the timed region
-    seeds = np.array(STABLE_SEEDS)[(np.arange(B_PER_GPU) + seed0) % len(STABLE_SEEDS)]
-    env = Burger(L=L_DOM, N=N, dt=DT, nu=NU, tend=TEND, case="turbulence", forcing=True, dforce=False, seed=seeds,
-                 nenvs=B_PER_GPU, device=device, history=False)
-    env.setup_basis(M, "hat")
-    rng = np.random.default_rng(seed0)
-    env.set_spectrum_reference(np.abs(rng.normal(1.0, 0.1, (int(TEND / DT) + 1, N // 2))) * 1e-3 + 1e-6)
-    return env
+def time_graph(torch, fn_steps, n_steps, reps=3, warm=2):
+    """Capture `fn_steps()` (which enqueues n_steps launches) into a CUDA graph; best-of-`reps` ms per step."""
+    g = torch.cuda.CUDAGraph()
+    fn_steps()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        fn_steps()
+    for _ in range(warm):
+        g.replay()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_steps
+        best = ms if best is None else min(best, ms)
+    del g
+    return best
+
+
+def pin_cores(local, world):
+    """One disjoint slice of the host cores per rank (all ranks of a node otherwise share the same affinity mask and
+    their launch threads migrate over each other)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if world > 1 and per >= 1:
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
+            return per
+    except Exception:
+        pass
+    return None
 
 
 def gpu_arm(args):
@@ -208,16 +300,19 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores_per_rank = pin_cores(local, world)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     K, W = args.steps, args.warmup
     pool = max(1, args.pool)
-    envs = [make_batch(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
+    make = make_batch_c5 if args.workload == "c5" else make_batch
+    B = 8192 if args.workload == "c5" else B_PER_GPU
+    envs = [make(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
     rng = np.random.default_rng(rank)
-    # one eddy-viscosity coefficient per environment, replicated over its M actions
-    acts_host = torch.from_numpy(np.repeat(rng.uniform(0.05, 0.1, (pool, B_PER_GPU, 1)), M, axis=2).copy()).pin_memory()
+    # eddy-viscosity coefficients: one value per (environment, action), positive (a stabilising closure)
+    acts_host = torch.from_numpy(rng.uniform(0.02, 0.1, (pool, B, M))).pin_memory()
     acts = acts_host.to(device)
     S = envs[0]._state_size
     RW = envs[0]._reward_buf.shape[1]
@@ -225,122 +320,62 @@ def gpu_arm(args):
     fused = world > 1 or args.fused_single      # --fused-single: 1-GPU diagnostic of the fused-gather overheads
     if fused:
         # Learner-side gather FUSED into the step kernel: every rank's kernel stores its state + reward rows straight
-        # into every rank's (double-buffered) gather buffer over NVLink and publishes a step flag; a 1-CTA wait kernel
-        # is the consumer side.  No NCCL call and no host work per step (marlpde_b200.dist.PeerGather.fuse).
+        # into every rank's (double-buffered) gather buffer over NVLink (one multimem.st per row on NVSwitch) and a
+        # 1-thread kernel behind it publishes the step / waits for the peers.  No NCCL call, no host work per step.
         from marlpde_b200.dist import PeerGather
         for env in envs:
-            pg = PeerGather(B_PER_GPU * (S + RW), torch.float64, device, copies=2)
-            pg.fuse(env, B_PER_GPU, S, RW, gather_state=not args.rewards_only)
+            pg = PeerGather(B * (S + RW), torch.float64, device, copies=2)
+            pg.fuse(env, B, S, RW, gather_state=not args.rewards_only)
             gathers.append(pg)
 
-    side = torch.cuda.Stream(device=device) if fused else None
-
-    def one_step(i, join=True):
+    def one_step(i):
         k = i % pool
-        st, rw = envs[k].step_n(acts[k], NSUB)
-        if fused and not args.no_wait:
-            # consumer side of the gather (all ranks' rows of this step have landed in this rank's buffer): it orders
-            # the LEARNER after the step, not the next batch's step kernel, so it runs on a forked stream and the
-            # step kernels stay back to back (programmatic dependent launch); joined once per rotation / step
-            main = torch.cuda.current_stream()
+        if fused:
+            # ONE library call: step kernel -> [side stream: publish + wait]; the main stream is free for the next batch
+            envs[k].step_n_fused(acts[k], NSUB, async_gather=True)
             gathers[k].step += 1
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                gathers[k].exchange_next()  # behind the kernel boundary: publish this rank's rows, wait for the peers' 
-            if join:
-                main.wait_stream(side)
-        return st, rw
-
-    def drain():
-        pass
+        else:
+            envs[k].step_n(acts[k], NSUB)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The pool rotation (one RL step of each of the `pool` batches) is captured once into a CUDA graph and replayed:
-    # the launch loop is host-bound otherwise (~14 us of Python per step_n call vs a ~16 us kernel).
-    graph, per_graph = None, 0
-    rot = pool * (2 if fused else 1)        # steps per graph: both copies of the double-buffered gather when fused
-    extra = 1 if fused and not args.no_wait else 0      # signal+wait kernel per step
-
-    def capture(chains, nsteps=None):
-        """Graph of one rotation (or of the first `nsteps` steps of it).  chains > 1: independent batches alternate between `chains` streams inside the graph, so
-        one batch's tail (and, multi-GPU, its gather stores draining over NVLink) overlaps the next batch's kernel; a single
-        chain serialises them (each kernel waits, through programmatic dependent launch, for its COMPLETE predecessor)."""
-        l_before = sum(e.launch_count for e in envs)
+    def capture(nsteps, chains, first=0):
+        """CUDA graph of RL steps first .. first+nsteps-1 of the pool rotation.  chains > 1: consecutive (independent)
+        batches alternate between `chains` streams inside the graph, so one batch's prologue / tail overlaps another
+        batch's sub-step loop (each chain serialises its own kernels through programmatic dependent launch)."""
+        l0 = sum(e.launch_count for e in envs)
         g_ = torch.cuda.CUDAGraph()
         cstreams = [torch.cuda.Stream(device=device) for _ in range(chains)] if chains > 1 else []
         with torch.cuda.graph(g_):
             cap = torch.cuda.current_stream()
             for cs in cstreams:
                 cs.wait_stream(cap)
-            nst = rot if nsteps is None else nsteps
-            for i in range(nst):
+            for i in range(first, first + nsteps):
                 if chains > 1:
                     with torch.cuda.stream(cstreams[i % chains]):
-                        one_step(i, join=False)
+                        one_step(i)
                 else:
-                    one_step(i, join=(i == nst - 1))
+                    one_step(i)
             for cs in cstreams:
                 cap.wait_stream(cs)
-            if chains > 1 and fused and not args.no_wait:
-                cap.wait_stream(side)
-        n_k = (sum(e.launch_count for e in envs) - l_before) + extra * nst
-        for g in gathers:                   # the capture pass only recorded: no step was published
-            g.step -= nst // pool
+            if fused:
+                for e in envs:
+                    e.peer_join()           # the graph ends when every batch's gather has completed
+        n_k = sum(e.launch_count for e in envs) - l0
         torch.cuda.synchronize()
         return g_, n_k
 
-    chains = max(1, args.chains)
-    if pool % chains:
-        chains = 1
-    if args.graph:
-        for i in range(rot):                # warm every batch before capture
-            one_step(i)
-        sync()
-        graph, per_graph = capture(chains)
-    # single GPU: the K % rot steps that do not fill a rotation get their own (shorter) graph instead of Python launches
-    tail_graph, tail_len, per_tail = None, 0, 0
-    if args.graph and not fused and K % rot:
-        tail_len = K % rot
-        tail_graph, per_tail = capture(1, tail_len)
-
-    def run_steps(first, n):
-        """n RL steps starting at rotation index `first` (a multiple of pool when the graph is used)."""
-        launched = 0
-        if graph is not None:
-            reps, n = divmod(n, rot)
-            for _ in range(reps):
-                graph.replay()
-            launched += reps * per_graph
-            for g in gathers:
-                g.step += reps * (rot // pool)
-            first += reps * rot
-            if tail_graph is not None and n == tail_len and first % pool == 0:
-                tail_graph.replay()
-                launched += per_tail
-                n = 0
-        l0 = sum(e.launch_count for e in envs)
-        for i in range(n):
-            one_step(first + i)
-        launched += sum(e.launch_count for e in envs) - l0 + extra * n
-        return launched
-
-    sampler = ClockSampler(local) if rank == 0 else None      # covers warm-up + timed + e2e regions
-    Wr = -(-W // rot) * rot if graph is not None else W        # whole rotations keep the graph aligned
-    run_steps(0, Wr)
+    chains = max(1, min(args.chains, pool))
+    # every batch once outside any graph (module load, lazy set-up, first-use allocations)
+    for i in range(pool):
+        one_step(i)
+    if fused:
+        for e in envs:
+            e.peer_join()
     sync()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    launches = run_steps(Wr, K)
-    ev1.record()
-    sync()
-    ms = ev0.elapsed_time(ev1)
-    for g in gathers:
-        g.check()
-    alive = all(int((e.status != 0).sum()) == 0 for e in envs)
 
     def new_episode():
         """Untimed: put every batch back at t = 0 (the forced N=32 LES only stays bounded for about one episode)."""
@@ -348,22 +383,88 @@ def gpu_arm(args):
             e.IC(case="turbulence")
         sync()
 
-    # extra (not the headline): the same K steps with TWO independent batches in flight inside the graph
-    ms2 = None
-    if args.graph and chains == 1 and pool % 2 == 0 and K >= rot:
+    # The timed region is ONE replay of a graph holding exactly K steps (K <= 960), else whole rotations + a tail graph.
+    seg = K if K <= 960 else pool * 8
+    graph, per_graph = capture(seg, chains)
+    tail_graph, per_tail = (None, 0)
+    if K % seg:
+        tail_graph, per_tail = capture(K % seg, chains)
+
+    def run_timed():
+        launched = 0
+        for _ in range(K // seg):
+            graph.replay()
+            launched += per_graph
+        if tail_graph is not None:
+            tail_graph.replay()
+            launched += per_tail
+        return launched
+
+    sampler = ClockSampler(local) if rank == 0 else None      # covers warm-up + timed + e2e regions
+    # warm-up: (a) >= 60 ms of the same graph so the SM clock has ramped before anything is timed, (b) a fresh episode,
+    # (c) the W steps the driver asks for (rounded up to whole replays of the graph)
+    t_ramp = time.perf_counter()
+    ramp_steps = 0
+    while time.perf_counter() - t_ramp < 0.06 and ramp_steps < 3000:
+        graph.replay()
+        ramp_steps += seg
+        torch.cuda.synchronize()
+    new_episode()
+    warm_steps = 0
+    while warm_steps < max(W, 3):
+        graph.replay()
+        warm_steps += seg
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launches = run_timed()
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    for g in gathers:
+        g.check()
+    alive_frac = float(np.mean([float((e.status == 0).double().mean()) for e in envs]))
+
+    # explanatory extra (not the headline): the same K steps strictly one batch after the other (one chain)
+    ms1 = None
+    if chains > 1 and not args.quick:
         new_episode()
-        graph1, per1 = graph, per_graph
-        graph, per_graph = capture(2)
-        run_steps(0, rot)
+        g1, _ = capture(seg, 1)
+        for _ in range(2):
+            g1.replay()
         sync()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev2.record()
-        run_steps(0, K - K % rot)
-        ev3.record()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        g1.replay()
+        e3.record()
         sync()
-        ms2 = ev2.elapsed_time(ev3) / (K - K % rot)
-        graph, per_graph = graph1, per1
-        alive = alive and all(int((e.status != 0).sum()) == 0 for e in envs)
+        ms1 = e2.elapsed_time(e3) / seg
+        del g1
+
+    # ---- shard invariance, driver-side evidence (untimed): rank 0 recomputes rows of other ranks locally ----------
+    gather_parity = None
+    if world > 1:
+        new_episode()
+        envs[0].step_n_fused(acts[0], NSUB)              # kernel -> publish -> wait, in stream order
+        gathers[0].step += 1
+        sync()
+        gathers[0].check()
+        if rank == 0:
+            cur = gathers[0].current()
+            ok = True
+            for r in sorted({1, world // 2, world - 1}):
+                twin = make(torch, device, 42 + 1000 * r)                          # rank r's batch 0, rebuilt here
+                a_r = torch.from_numpy(np.random.default_rng(r).uniform(0.02, 0.1, (pool, B, M))[0]).to(device)
+                st, rw = twin.step_n(a_r, NSUB)
+                torch.cuda.synchronize()
+                rows = slice(0, B, max(1, B // 64))
+                got_rw = cur[r][B * S:].view(B, RW)
+                ok = ok and bool(torch.equal(got_rw[rows], rw[rows]))
+                if not args.rewards_only:
+                    ok = ok and bool(torch.equal(cur[r][:B * S].view(B, S)[rows], st[rows]))
+                del twin
+            gather_parity = ok
+        sync()
     new_episode()
 
     # ---- end to end through the public API with HOST buffers --------------------------------
@@ -371,20 +472,18 @@ def gpu_arm(args):
     # reward -> the host waits for them before that batch gets its next actions.  The learner keeps
     # `depth` independent batches in flight (marlpde_b200.pipeline.HostPipeline) so PCIe transfers of one
     # batch overlap the kernel of another; each batch's own action->state chain stays strictly serial.
+    # Multi-GPU: the kernel still stores its rows into every rank's gather buffer; each rank PUBLISHES behind its step
+    # (1-thread kernel on the slot's stream, no wait) and only the learner rank waits for the peers, on its own stream.
     from marlpde_b200.pipeline import HostPipeline
     depth = min(pool, max(1, args.depth))
-    drain()
+    learner = torch.cuda.Stream(device=device) if (fused and rank == 0) else None
 
-    def gather(k, st, rw):            # N > 1: the fused gather stays part of every step; copy out this step's rows
-        g = gathers[k]
-        g.step += 1
-        g.exchange_next()
-        if st is None:                  # host path of the library already copied this rank's rows out
-            return None
-        mine = g.current()[rank]
-        return mine[:B_PER_GPU * S].view(B_PER_GPU, S), mine[B_PER_GPU * S:].view(B_PER_GPU, RW)
+    def publish(k, st, rw):
+        gathers[k].step += 1
+        gathers[k].signal_next()
+        return None
 
-    pipe = HostPipeline(envs[:depth], NSUB, post_step=gather if fused else None)
+    pipe = HostPipeline(envs[:depth], NSUB, post_step=publish if fused else None)
     for k in range(depth):
         pipe.act_host[k].copy_(acts_host[k])
     Ke = max(depth, min(K, 2000))
@@ -397,95 +496,232 @@ def gpu_arm(args):
             st_h, rw_h = pipe.collect(k)              # results of this batch's previous step are on the host
             checksum += float(rw_h[0, 0])             # the host really reads them
             pipe.submit(k)                            # next actions for this batch (already in pinned memory)
+            if learner is not None:
+                learner.wait_event(pipe.done[k])
+                with torch.cuda.stream(learner):
+                    gathers[k].wait_next()
         pipe.drain()
+        if learner is not None:
+            learner.synchronize()
 
     e2e_round(3 * depth)
     sync()
     t0 = time.perf_counter()
     e2e_round(Ke)
+    torch.cuda.synchronize()
+    e2e_local = time.perf_counter() - t0
     sync()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = e2e_local
     clocks = sampler.stop() if sampler else None
+    for g in gathers:
+        g.poll()
 
+    per_rank_e2e = None
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3, ms2 or 0.0], device=device, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s * 1e3, ms1 or 0.0, -alive_frac], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
-        ms2 = float(t[2]) if ms2 is not None else None
-        ok = torch.tensor([1 if alive else 0], device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        alive = bool(ok.item())
+        ms1 = float(t[2]) if ms1 is not None else None
+        alive_frac = -float(t[3])
+        allt = [torch.zeros(1, device=device, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allt, torch.tensor([e2e_local * 1e6 / Ke], device=device, dtype=torch.float64))
+        per_rank_e2e = [round(float(x), 2) for x in allt]
 
     if rank == 0:
-        total_envs = B_PER_GPU * world
+        total_envs = B * world
         value = total_envs * NSUB * K / (ms * 1e-3)
         peak, how = peaks()
+        facts = kernel_facts()
         per_launch_s = ms * 1e-3 / K
-        achieved = B_PER_GPU * BYTES_PER_ENV_LAUNCH / per_launch_s / 1e9
+        bytes_env = BYTES_C5 if args.workload == "c5" else BYTES_PER_ENV_LAUNCH
+        achieved = B * bytes_env / per_launch_s / 1e9
+        fp64_peak = float(facts.get("fp64_peak_tflops", 33.2))
+        tf = B * NSUB * FLOPS_PER_ENV_STEP / per_launch_s / 1e12
+        cfg = workload_config(world)
+        if args.workload == "c5":
+            cfg["workload"] = (f"MARL Burgers N={N} x {B} envs/GPU (BASELINE configs[4]), fp64, {N} per-gridpoint agents (state windows "
+                               f"of 3, one eddy-viscosity action each), MSE reward vs a shared truth table, nIntermediate={NSUB}; 4-lane teams")
+            cfg["envs_per_gpu"], cfg["global_envs"] = B, B * world
         line = {
             "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": workload_config(world, ("multicast (multimem.st, %s memory)" if gathers[0].multicast else "unicast peer (%s memory)")
-                                      % gathers[0].backend if gathers else None),
+            "data": "synthetic", "config": cfg,
+            "timing": {"how": f"{K} steps = ONE replay of a CUDA graph holding exactly {K} launches (pool rotation)" if K <= 960 else
+                              f"{K // seg} replays of a {seg}-step graph + a {K % seg}-step tail graph",
+                       "batches_in_flight": chains,
+                       "warmup_steps_run": int(warm_steps), "clock_ramp_steps": int(ramp_steps),
+                       "note": "the step kernels of consecutive (independent) batches alternate between `batches_in_flight` "
+                               "streams inside the graph; device time by CUDA events around the replay, max over ranks"},
             "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                    "steps": Ke, "batches_in_flight": depth,
+                    "steps": Ke, "batches_in_flight": depth, "us_per_step_per_rank": per_rank_e2e,
+                    "cores_per_rank": cores_per_rank,
                     "note": "per RL step of a batch: pinned host actions -> H2D -> step_n -> D2H state+reward -> host waits; "
-                            "independent batches overlap (HostPipeline)"},
+                            "independent batches overlap (HostPipeline)" +
+                            ("; multi-GPU: rows also stored into every rank's gather buffer, each rank publishes behind its step, "
+                             "only the learner rank (0) waits for the peers" if fused else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": how,
-                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,HOT>",
-                         "bytes_per_launch": B_PER_GPU * BYTES_PER_ENV_LAUNCH,
+                         "traffic": facts.get("traffic_bytes_per_launch", {}).get("c5" if args.workload == "c5" else "c2"),
+                         "traffic_source": facts.get("traffic_source"), "peak_source": how,
+                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,HOT>" if args.workload != "c5"
+                                   else "burgers_warp_kernel<double,32,4,generic>",
+                         "bytes_per_launch": B * bytes_env,
                          "launch_us": per_launch_s * 1e6,
-                         "note": "algorithmic bytes = 1912 B per env per launch (SURVEY 8d) x 4096 envs; the 10 solver "
-                                 "steps fused into one launch keep the state on chip, so the launch is bound by FP64 + "
-                                 "shuffle issue and their latencies, not by HBM (see roofline_fp64, DESIGN.md 5, profiles/)"},
-            "roofline_fp64": {"bound": "fp64", "achieved": B_PER_GPU * NSUB * FLOPS_PER_ENV_STEP / per_launch_s / 1e12,
-                              "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                              "frac": B_PER_GPU * NSUB * FLOPS_PER_ENV_STEP / per_launch_s / 1e12 / FP64_PEAK_TFLOPS,
-                              "peak_source": "measured (tools/microbench.cu DFMA loop)",
+                         "launch_us_one_batch_at_a_time": None if ms1 is None else ms1 * 1e3,
+                         "note": f"algorithmic bytes = {bytes_env} B per env per launch (SURVEY 8d) x {B} envs; launch_us = timed region / "
+                                 "launches (kernels of independent batches overlap); the 10 solver steps fused into one launch keep the "
+                                 "state on chip, so the launch is bound by FP64 + shuffle issue and their latencies, not by HBM: even at "
+                                 "the FP64 peak the launch would take 3.2 us = 0.37 of the HBM roofline (see roofline_fp64, sweep, DESIGN.md 5)"},
+            "roofline_fp64": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                              "peak_source": facts.get("fp64_peak_source", "measured (tools/microbench.cu DFMA loop, profiles/r1_microbench_b200.md)"),
                               "note": "2.6 kflop per env-step (SURVEY 8d) x 40960 env-steps per launch"},
-            "all_envs_alive": alive,
-            "two_batches_in_flight": None if ms2 is None else {
-                "ms_per_step": ms2, "value": total_envs * NSUB / (ms2 * 1e-3), "unit": "env-steps/s",
-                "note": "same steps with two independent batches alternating between two streams inside the replayed graph "
-                        "(one batch's tail overlaps the next batch's kernel); not used for value / roofline"},
+            "all_envs_alive": alive_frac == 1.0, "alive_fraction": alive_frac,
         }
+        if world > 1:
+            line["gather_parity"] = gather_parity
+            line["transport"] = (("NVSwitch multicast (multimem.st), %s memory" if gathers[0].multicast else "unicast peer stores, %s memory")
+                                 % gathers[0].backend) + (", rewards only" if args.rewards_only else "")
+        if world == 1 and not args.quick:
+            del pipe
+            envs.clear()
+            torch.cuda.empty_cache()
+            try:
+                line["sweep"] = batch_sweep(torch, device)
+            except Exception as e:          # the extras never take the headline down
+                line["sweep"] = {"error": repr(e)}
+            try:
+                line["other_configs"] = other_configs(torch, device)
+            except Exception as e:
+                line["other_configs"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
-            v, cores, steps, wall = cpu_run(seconds=args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cores} single-env numpy-port processes x {args.cpu_seconds:.0f} s of the same "
-                                              f"workload (N=32, forcing, eddy action, spectral reward, one step() per call)"}
+            v, cores, kind, sample = cpu_run(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- driver-run extras (N = 1)
+def batch_sweep(torch, device):
+    """Bench workload at other batch sizes / fused-step counts (the HBM roofline is the bound of the per-step-I/O
+    regime, the FP64 roofline of the fused regime).  Each entry: one CUDA graph over a pool of batches larger than L2."""
+    peak, _ = peaks()
+    fp64_peak = float(kernel_facts().get("fp64_peak_tflops", 33.2))
+    out = []
+    spec = spectrum_table()
+    for B, nsub, lanes in ((4096, 10, 8), (8192, 10, 4), (32768, 10, 4), (32768, 1, 4), (131072, 1, 4)):
+        per_batch = B * 1912
+        pool = max(2, -(-160_000_000 // per_batch))
+        envs = [make_batch(torch, device, 7 + i, B=B, team_lanes=lanes, spec=spec) for i in range(pool)]
+        a = torch.from_numpy(np.random.default_rng(B).uniform(0.02, 0.1, (B, M))).to(device)
+        reps = max(1, 40 // pool)
+
+        def steps():
+            for _ in range(reps):
+                for e in envs:
+                    e.step_n(a, nsub)
+        ms = time_graph(torch, steps, reps * pool)
+        alive = all(int((e.status != 0).sum()) == 0 for e in envs)
+        gbs = per_batch / (ms * 1e-3) / 1e9
+        tf = B * nsub * FLOPS_PER_ENV_STEP / (ms * 1e-3) / 1e12
+        out.append({"envs": B, "n_sub": nsub, "lanes_per_env": lanes, "launch_us": ms * 1e3,
+                    "env_steps_per_s": B * nsub / (ms * 1e-3), "hbm_frac": gbs / peak, "fp64_frac": tf / fp64_peak,
+                    "all_envs_alive": alive})
+        del envs
+        torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(torch, device):
+    """BASELINE configs[2], [3], [4] on one GPU, measured in-process after the headline (each < 1 s of GPU time)."""
+    from marlpde_b200 import Burger, KS
+    peak, _ = peaks()
+    fp64_peak = float(kernel_facts().get("fp64_peak_tflops", 33.2))
+    res = {}
+    rng = np.random.default_rng(0)
+    # ---- C3: KS L=22 N=64 x 8192, M=64 hat basis, 10 ETDRK4 steps + state per launch
+    B, n, m = 8192, 64, 64
+    pool = [KS(L=22, N=n, dt=0.25, nsteps=100000, nenvs=B, u0=rng.normal(0, 1e-3, (B, n)), history=False, device=device)
+            for _ in range(6)]
+    for k in pool:
+        k.setup_basis(m, "hat")
+    a = torch.as_tensor(rng.normal(0, 1e-3, (B, m)), device=device)
+
+    def ks_steps():
+        for k in pool:
+            k.step_n(a, 10, want_reward=False)
+    ms = time_graph(torch, ks_steps, len(pool))
+    res["c3_ks_n64_x8192"] = {"launch_us": ms * 1e3, "value": B * 10 / (ms * 1e-3), "unit": "env-steps/s", "n_sub": 10,
+                              "hbm_frac": B * BYTES_KS / (ms * 1e-3) / 1e9 / peak,
+                              "fp64_frac": B * 10 * FLOPS_KS_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
+                              "alive": all(int((k.status != 0).sum()) == 0 for k in pool)}
+    del pool
+    torch.cuda.empty_cache()
+    # ---- C4: Burgers DNS N=1024 x 512, 500 steps per launch, u / v / Ek history rows every step
+    B, n, steps = 512, 1024, 500
+    dns = Burger(L=L_DOM, N=n, dt=DT, nu=NU, nsteps=steps, case="turbulence", seed=100 + np.arange(B) % 4, nenvs=B, history=True,
+                 device=device)
+
+    def dns_run():
+        dns.IC(case="turbulence", on_device=True)
+        dns.step_n(None, steps, want_state=False, want_reward=False)
+    dns_run()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(2):
+        dns.IC(case="turbulence", on_device=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dns.step_n(None, steps, want_state=False, want_reward=False)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        best = t if best is None else min(best, t)
+    hist_bytes = B * steps * (n * 8 + n * 8 + (n // 2 + 1) * 8)
+    res["c4_dns_n1024_x512"] = {"launch_us": best * 1e3, "value": B * steps / (best * 1e-3), "unit": "env-steps/s", "n_sub": steps,
+                                "history": "uu f64 + vv complex64 + Ek_ktt f64 rows every step",
+                                "hbm_frac": hist_bytes / (best * 1e-3) / 1e9 / peak,
+                                "fp64_frac": B * steps * FLOPS_DNS_STEP / (best * 1e-3) / 1e12 / fp64_peak,
+                                "alive": int((dns.status != 0).sum()) == 0}
+    del dns
+    torch.cuda.empty_cache()
+    # ---- C5 per GPU: MARL Burgers N=32 x 8192, 32 agents, MSE reward, 4-lane teams
+    B = 8192
+    pool = [make_batch_c5(torch, device, 42 + i, B=B) for i in range(10)]
+    a5 = torch.as_tensor(rng.uniform(0.0, 0.02, (B, M)), device=device)
+
+    def c5_steps():
+        for e in pool:
+            e.step_n(a5, NSUB)
+    ms = time_graph(torch, c5_steps, len(pool))
+    res["c5_marl_n32_x8192_per_gpu"] = {"launch_us": ms * 1e3, "value": B * NSUB / (ms * 1e-3), "unit": "env-steps/s", "n_sub": NSUB,
+                                        "hbm_frac": B * BYTES_C5 / (ms * 1e-3) / 1e9 / peak,
+                                        "fp64_frac": B * NSUB * FLOPS_PER_ENV_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
+                                        "alive": all(int((e.status != 0).sum()) == 0 for e in pool)}
+    del pool
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--depth", type=int, default=8, help="e2e: independent batches in flight")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the sweep / other-config / single-chain extras")
     ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")
-    ap.add_argument("--no-wait", action="store_true", help="diagnostic: skip the consumer-side wait kernels")
-    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every step from Python instead of "
-                    "replaying the captured pool rotation")
-    ap.add_argument("--chains", type=int, default=1, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--chains", type=int, default=2, help="independent batches in flight inside the replayed graph")
     ap.add_argument("--rewards-only", action="store_true", help="multi-GPU: gather only the rewards (configs[4] wording)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")
     args = ap.parse_args()
-    if args.workload == "c5":
-        global WORKLOAD, B_PER_GPU, BYTES_PER_ENV_LAUNCH
-        WORKLOAD, B_PER_GPU = "c5", 8192
-        BYTES_PER_ENV_LAUNCH = 8 * (M + 4 * (N + 2) + 3 * N + N)        # 2368 B
     if args.impl == "reference":
         reference_arm(args)
     else:

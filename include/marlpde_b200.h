@@ -157,6 +157,16 @@ int mpde_reset_handoff(mpde_env* env, const void* vsrc_dev, int64_t nsrc, int32_
 int mpde_reset_turbulence(mpde_env* env, const int64_t* seed_dev, const double* offset_dev, const double* x_dev,
                           const double* amp_dev, const uint8_t* mask_dev, void* stream);
 
+/* Stochastic-forcing tables on the device (Burger.py:66, 88-89, 94-95): for each of the n seeds (DEVICE int64,
+ * values in [0, 2^32): NumPy's init_genrand seeding) reproduce `np.random.seed(seed)`; [nunoise: nu = 0.01 + 0.02 *
+ * np.random.uniform()]; `randfac1 = np.random.normal(size=(32, nsteps))`; `randfac2 = ...` and return the only entries
+ * the solver reads (Burger.py:416-419): r1_dev / r2_dev [n, 3, stepper] = rows 1..3, columns < stepper (DEVICE double),
+ * nu_dev [n] when nunoise (else may be NULL).  Which candidates the polar method accepts is bit-identical to NumPy; the
+ * kept values agree to the last bit of log() (<= 1 ulp).  One warp per seed, ~2 ms per 4096 seeds at nsteps = 5000. */
+int mpde_forcing_tables(const int64_t* seeds_dev, int64_t n, int32_t nsteps, int32_t stepper, int32_t nunoise, double* r1_dev,
+                        double* r2_dev, double* nu_dev, void* stream);
+const char* mpde_rng_last_error(void);
+
 /* Ground truth for the MSE reward at scale: sample the tensor-product B-spline that
  * setGroundTruth builds (Burger.py:322-323; FITPACK knots tx [ntx], ty [nty], coefficients c [(ntx-kx-1)*(nty-ky-1)],
  * degrees kx, ky in 1..3 -- all DEVICE double arrays) at out[q, i, j] = S(xq[q, j], tq[i]) for nq shifted grids of N points
@@ -202,8 +212,13 @@ int64_t mpde_launch_count(const mpde_env* env);
  *   export/open  : 64-byte IPC handle of a buffer / map a peer's buffer into this process
  *   put          : copy `nbytes` from `src` into EVERY rank's gather buffer at `dst_offset_bytes`, then publish
  *                  `step` in slot `my_rank` of every rank's flag array (int64 [nranks])
- *   wait         : make `stream` wait until all slots of this rank's flag array are >= step; bounded by
- *                  `max_spins` polls per source -- a missing peer sets *err_dev = 1 + rank instead of hanging */
+ *   wait         : make `stream` wait until all slots of this rank's flag array are >= step; bounded in TIME:
+ *                  a peer that has not published after `timeout_us` microseconds (<= 0: MPDE_PEER_TIMEOUT_S seconds,
+ *                  default 30) sets *err = 1 + rank instead of hanging.  A timed-out wait_next / exchange_next does NOT
+ *                  advance the expected step, and once *err is set later waits give up after 1 ms, so a dead peer costs
+ *                  one timeout.  `err` may be device memory or mapped pinned host memory (mpde_host_flag_alloc), which
+ *                  the host can poll without synchronising.
+ *   host_flag_*  : int32 [n] of zero-initialised mapped pinned host memory (device-accessible under UVA) */
 int mpde_peer_alloc(size_t bytes, void** out);
 int mpde_peer_free(void* p);
 int mpde_peer_export(void* dev_ptr, void* handle64);
@@ -211,7 +226,9 @@ int mpde_peer_open(const void* handle64, void** out);
 int mpde_peer_close(void* p);
 int mpde_peer_put(const void* src, size_t nbytes, void* const* dst_ptrs, size_t dst_offset_bytes, void* const* flag_ptrs,
                   int32_t my_rank, int32_t nranks, int64_t step, void* counter_dev, void* stream);
-int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err_dev, int64_t max_spins, void* stream);
+int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err, int64_t timeout_us, void* stream);
+int mpde_host_flag_alloc(int32_t n_int32, void** out);
+int mpde_host_flag_free(void* p);
 const char* mpde_peer_last_error(void);
 
 /* Gather FUSED into the step kernel (warp-resident Burgers kernels, N <= 256): after this call every mpde_step of
@@ -236,10 +253,28 @@ int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs,
  * the copy of the current parity).  local_reward = local_state + B*S for the packed single-copy path. */
 int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward);
 int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream);
-int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
+int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err, int64_t timeout_us, void* stream);
 /* signal_next + wait_next as ONE kernel launch */
 int mpde_peer_exchange_next(void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
-                            void* expect_dev, void* err_dev, int64_t max_spins, void* stream);
+                            void* expect_dev, void* err, int64_t timeout_us, void* stream);
+
+/* One RL step of this rank's shard INCLUDING the gather, as ONE host call (the multi-GPU form of the loop body of
+ * burger_environment.py:148-176): step kernel with the fused peer stores -> publish -> wait for every rank's rows.
+ *   mpde_set_peer_sync : once, after mpde_set_peer_output -- the arguments mpde_peer_exchange_next takes.
+ *   mpde_step_fused    : async_gather = 0: kernel and exchange run in stream order on `stream`, replayed from a CUDA graph
+ *                        cached per (buffers, nsub, parity) -- one driver call per RL step; work enqueued behind it sees
+ *                        the gathered rows of ALL ranks.  async_gather = 1: the exchange runs on a side stream the
+ *                        library owns, forked behind the step kernel, so `stream` is free for the next independent
+ *                        batch; mpde_peer_join(env, s) makes stream s wait for the last exchange (the caller may
+ *                        capture step_fused(async) ... peer_join into a CUDA graph of its own).
+ * A step that fails to launch does not flip the parity of the double-buffered gather copies.
+ * mpde_step(nsub = 0) stays available with a gather bound (getState / getMseReward of the current state at episode
+ * reset): it writes the caller's local buffers only and publishes nothing. */
+int mpde_set_peer_sync(mpde_env* env, void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
+                       void* expect_dev, void* err, int64_t timeout_us);
+int mpde_step_fused(mpde_env* env, const void* actions_dev, int32_t nsub, void* state_out, void* reward_out, int32_t async_gather,
+                    void* stream);
+int mpde_peer_join(mpde_env* env, void* stream);
 
 const char* mpde_last_error(void);
 int mpde_abi_version(void);

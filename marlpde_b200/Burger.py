@@ -65,7 +65,20 @@ class Burger(SpectralEnv):
         need_tables = self.forcing or case == 'forced' or nunoise
         uniq = np.unique(self.seeds)
         r1 = r2 = None
-        if need_tables:
+        self._tables_on_device = False
+        if need_tables and len(uniq) > 16 and case != 'forced' and int(uniq.min()) >= 0 and int(uniq.max()) < 2 ** 32:
+            # many distinct seeds (seed = 42 + e): the NumPy stream of every seed is reproduced on the device
+            # (mpde_forcing_tables, one warp per seed); only rows 1..3 / columns < stepper exist -- all the solver reads
+            # (Burger.py:416-419) -- the other rows of the [B, 32, stepper] tables are NaN
+            nu_u, a3, b3 = device_forcing_tables(uniq, nsteps, self.stepper, nunoise, device)
+            inv = np.searchsorted(uniq, self.seeds)
+            r1 = np.full((B, 32, self.stepper), np.nan)
+            r2 = np.full((B, 32, self.stepper), np.nan)
+            r1[:, 1:4], r2[:, 1:4] = a3[inv], b3[inv]
+            if nunoise:
+                nus = nu_u[inv]
+            self._tables_on_device = True
+        elif need_tables:
             per_seed = {}
             for sd in uniq:
                 rs = np.random.RandomState(int(sd))
@@ -276,6 +289,9 @@ class Burger(SpectralEnv):
         if actions is None:
             return None
         assert self.basis is not None, "[Burger] Basis not set up (is None)."
+        if (isinstance(actions, torch.Tensor) and actions.device == self.device and actions.dtype == self.dtype and actions.dim() == 2
+                and actions.shape[0] == self.nenvs and actions.shape[1] == self.M and actions.is_contiguous()):
+            return actions                                                 # the learner's own [B,M] device tensor: no copy
         if isinstance(actions, torch.Tensor):
             a = actions.to(device=self.device, dtype=self.dtype)
         else:
@@ -310,6 +326,28 @@ class Burger(SpectralEnv):
         if rw is not None:
             self._reward_at = self.ioutnum
         return st, rw
+
+    def _reward_enabled(self):
+        return self._spec_ref is not None or self._truth_shift is not None
+
+    def step_n_fused(self, actions, n, async_gather=False):
+        """Multi-GPU form of step_n with a fused gather bound (dist.PeerGather.fuse): step kernel storing the rows into every
+        rank's buffer -> publish -> wait for all ranks, as ONE library call replayed from a cached CUDA graph
+        (mpde_step_fused).  ``async_gather``: the publish / wait pair runs on a side stream; ``peer_join()`` orders the
+        current stream behind it."""
+        self._upload_forcing()
+        a = self._actions(actions)
+        L_check(self._lib.mpde_step_fused(self._h, self._ptr(a), int(n), self._ptr(self._state_buf), self._ptr(self._reward_buf),
+                                          1 if async_gather else 0, self._stream()))
+        self.stepnum += n
+        self.ioutnum += n
+        for _ in range(n):
+            self.t += self.dt
+        self._state_at = self._reward_at = -1                              # this step's rows live in the gather copy
+        return None
+
+    def peer_join(self):
+        L_check(self._lib.mpde_peer_join(self._h, self._stream()))
 
     def step_n_host(self, actions_host, n, state_host, reward_host=None, stream=None, packed_out=None):
         """Host-buffer form of step_n for a host-side policy: (pinned) host actions [B,M] in, (pinned) host
@@ -410,6 +448,26 @@ class Burger(SpectralEnv):
 
 def _np(a):
     return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
+def device_forcing_tables(seeds, nsteps, stepper, nunoise=False, device=None):
+    """randfac1[1:4, :stepper], randfac2[1:4, :stepper] (and nu when ``nunoise``) of ``np.random.seed(seed)`` for every
+    seed, generated on the device (Burger.py:66,88-95; mpde_forcing_tables).  Returns (nu [n] or None, r1 [n,3,s], r2 [n,3,s])."""
+    lib = LB.lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError("marlpde_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    sd = torch.as_tensor(np.asarray(seeds, dtype=np.int64), device=dev).contiguous()
+    n = sd.numel()
+    r1 = torch.empty((n, 3, stepper), dtype=torch.float64, device=dev)
+    r2 = torch.empty_like(r1)
+    nu = torch.empty((n,), dtype=torch.float64, device=dev) if nunoise else None
+    with torch.cuda.device(dev):
+        rc = lib.mpde_forcing_tables(sd.data_ptr(), n, int(nsteps), int(stepper), 1 if nunoise else 0, r1.data_ptr(), r2.data_ptr(),
+                                     nu.data_ptr() if nunoise else None, torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        raise RuntimeError("marlpde_b200: " + lib.mpde_rng_last_error().decode())
+    return (nu.cpu().numpy() if nunoise else None), r1.cpu().numpy(), r2.cpu().numpy()
 
 
 L_DFORCE, L_FORCING, L_SSM, L_DSM = LB.DFORCE, LB.FORCING, LB.SSM, LB.DSM

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mpde_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mpde_reset_handoff": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mpde_reset_turbulence": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mpde_forcing_tables": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mpde_rng_last_error": (C.c_char_p, []),
     "mpde_eval_spline_table": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _vp]),
     "mpde_step_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mpde_step_host_packed": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
@@ -66,6 +68,11 @@ SIGNATURES = {
     "mpde_peer_put": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), C.c_size_t, C.POINTER(_vp), _i32, _i32, _i64, _vp, _vp]),
     "mpde_peer_wait": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp]),
     "mpde_peer_last_error": (C.c_char_p, []),
+    "mpde_host_flag_alloc": (C.c_int, [_i32, C.POINTER(_vp)]),
+    "mpde_host_flag_free": (C.c_int, [_vp]),
+    "mpde_set_peer_sync": (C.c_int, [_vp, C.POINTER(_vp), _i32, _vp, _vp, _i32, _vp, _vp, _i64]),
+    "mpde_step_fused": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "mpde_peer_join": (C.c_int, [_vp, _vp]),
     "mpde_set_peer_output": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp]),
     "mpde_set_peer_local": (C.c_int, [_vp, _vp, _vp]),
     "mpde_peer_signal_next": (C.c_int, [C.POINTER(_vp), _i32, _vp, _vp]),

@@ -57,6 +57,10 @@ struct mpde_env {
     virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
                                 void* mc_reward) = 0;
     virtual int set_peer_local(void* state, void* reward) = 0;
+    virtual int set_peer_sync(void* const* flag_slots, int n, void* step_dev, const void* my_flags, int nranks, void* expect_dev,
+                              void* err, int64_t timeout_us) = 0;
+    virtual int step_fused(const void* actions, int nsub, void* state_out, void* reward_out, int async, cudaStream_t st) = 0;
+    virtual int peer_join(cudaStream_t st) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -89,11 +93,15 @@ struct Env : mpde_env {
     }
     template <typename U>
     int upload(U* dst, const std::vector<U>& src) {
+        // the tables may be read by step kernels in flight on non-blocking streams, which a legacy-stream copy does
+        // not order against: drain the device first (set-up path, once per episode at most)
+        CU(cudaDeviceSynchronize());
         CU(cudaMemcpy(dst, src.data(), src.size() * sizeof(U), cudaMemcpyHostToDevice));
         return 0;
     }
     ~Env() override {
         for (const HostGraph& g : host_graphs) cudaGraphExecDestroy(g.exec);
+        if (sync.side) { cudaStreamDestroy(sync.side); cudaEventDestroy(sync.ev_fork); cudaEventDestroy(sync.ev_join); }
         for (void* p : owned) cudaFree(p);
     }
 
@@ -392,11 +400,15 @@ struct Env : mpde_env {
         if (nsub == 0) flags |= F_NO_ADVANCE;
         if (aux_flags & 1) flags |= (1 << 8);       // F_KS_UUROW
         p.flags = flags;
-        if (peer_bound) {
-            if (!state_out || !reward_out || nsub == 0)
-                return fail("step: a fused peer gather is bound (mpde_set_peer_output): every call must advance and write state and reward");
+        const bool peer_step = peer_bound && nsub > 0;
+        if (peer_bound && nsub == 0) {
+            // getState() / getMseReward() of the current state (episode reset, diagnostics): written to the caller's
+            // LOCAL buffers only -- no peer stores, no parity flip, nothing is published
+            p.peer = PeerSink{};
+        } else if (peer_bound) {
+            if (!state_out || !reward_out)
+                return fail("step: a fused peer gather is bound (mpde_set_peer_output): an advancing call must write state and reward");
             p.peer.parity = (int)(peer_steps & 1);
-            ++peer_steps;
         }
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
@@ -417,6 +429,7 @@ struct Env : mpde_env {
         if (rc < 0) return fail("step: unsupported N for this equation (power of two, 8..2048)");
         launches += rc;
         CU(cudaGetLastError());
+        if (peer_step) ++peer_steps;      // only a step that really launched flips the parity of the gather copies
         return 0;
     }
 
@@ -430,7 +443,9 @@ struct Env : mpde_env {
     // graph and replayed by later calls: one driver call per RL step instead of four (MPDE_HOST_GRAPH=0 disables;
     // a stream that is already being captured by the caller, or the legacy default stream, gets the plain chain).
     struct HostGraph {
-        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec; bool packed; int parity;
+        const void* actions; void* state; void* reward; int nsub; int64_t epoch; int kernels; cudaGraphExec_t exec;
+        int kind;       // 0 host buffers, 1 host buffers with one packed output copy, 2 fused multi-GPU step (device buffers)
+        int parity;
     };
     std::vector<HostGraph> host_graphs;
     int step_host_enqueue(const void* actions, int nsub, void* state_out, void* reward_out, size_t na, size_t ns, size_t nr,
@@ -465,38 +480,126 @@ struct Env : mpde_env {
         if (st) CU(cudaStreamIsCapturing(st, &cs));
         if (!use_graph || !st || st == cudaStreamLegacy || cs != cudaStreamCaptureStatusNone)
             return step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
-        for (const HostGraph& g : host_graphs)
-            if (g.actions == actions && g.state == state_out && g.reward == reward_out && g.nsub == nsub && g.epoch == epoch &&
-                g.packed == packed_out && g.parity == parity) {
-                CU(cudaGraphLaunch(g.exec, st));
-                if (peer_bound) ++peer_steps;
-                launches += g.kernels;
-                return 0;
-            }
-        const int64_t l0 = launches;
+        {
+            int rc = 0;
+            if (find_and_launch(HostGraph{actions, state_out, reward_out, nsub, epoch, 0, nullptr, packed_out ? 1 : 0, parity}, st, rc)) return rc;
+        }
+        return capture_and_launch(HostGraph{actions, state_out, reward_out, nsub, epoch, 0, nullptr, packed_out ? 1 : 0, parity}, st,
+                                  [&] { return step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st); });
+    }
+    // Capture what `enqueue` puts on `st` into a graph, cache it under `key` and launch it once.  The capture pass only
+    // records: the parity counter of a bound gather moves when the graph is LAUNCHED, and is rolled back on any failure.
+    template <typename F>
+    int capture_and_launch(HostGraph key, cudaStream_t st, F enqueue) {
+        const int64_t l0 = launches, ps0 = peer_steps;
         CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int rc = step_host_enqueue(actions, nsub, state_out, reward_out, na, ns, nr, st);
+        const int rc = enqueue();
         const std::string first_err = g_err;
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        const int kernels = (int)(launches - l0);
+        key.kernels = (int)(launches - l0);
         launches = l0;
+        peer_steps = ps0;
         if (rc != 0 || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
-            return rc != 0 ? fail(first_err) : fail(std::string("step_host: graph capture failed: ") + cudaGetErrorString(ce));
+            return rc != 0 ? fail(first_err) : fail(std::string("graph capture failed: ") + cudaGetErrorString(ce));
         }
-        cudaGraphExec_t exec = nullptr;
-        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        const cudaError_t ie = cudaGraphInstantiate(&key.exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) return fail(std::string("step_host: cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+        if (ie != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
         if (host_graphs.size() >= 8) {
             cudaGraphExecDestroy(host_graphs.front().exec);
             host_graphs.erase(host_graphs.begin());
         }
-        host_graphs.push_back(HostGraph{actions, state_out, reward_out, nsub, epoch, kernels, exec, packed_out, parity});
-        CU(cudaGraphLaunch(exec, st));
-        launches += kernels;
+        host_graphs.push_back(key);
+        CU(cudaGraphLaunch(key.exec, st));
+        launches += key.kernels;
+        if (peer_bound && key.nsub > 0) ++peer_steps;
+        return 0;
+    }
+    bool find_and_launch(const HostGraph& key, cudaStream_t st, int& rc) {
+        for (const HostGraph& g : host_graphs)
+            if (g.actions == key.actions && g.state == key.state && g.reward == key.reward && g.nsub == key.nsub && g.epoch == epoch &&
+                g.kind == key.kind && g.parity == key.parity) {
+                const cudaError_t e = cudaGraphLaunch(g.exec, st);
+                if (e != cudaSuccess) { rc = fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e)); return true; }
+                if (peer_bound && g.nsub > 0) ++peer_steps;
+                launches += g.kernels;
+                rc = 0;
+                return true;
+            }
+        return false;
+    }
+
+    // ---- fused multi-GPU step: kernel (+ peer stores) -> publish -> wait, ONE host call ---------------------------------
+    struct PeerSync {
+        void* slots[16] = {};
+        int n = 0, nranks = 0;
+        void *step_dev = nullptr, *expect_dev = nullptr, *err = nullptr;
+        const void* my_flags = nullptr;
+        int64_t timeout_us = 0;
+        bool set = false;
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        bool pending_join = false;
+    } sync;
+    int set_peer_sync(void* const* flag_slots, int n, void* step_dev, const void* my_flags, int nranks, void* expect_dev, void* err,
+                      int64_t timeout_us) override {
+        if (!flag_slots && n == 0) { sync.set = false; return 0; }
+        if (n < 1 || n > 16 || nranks < 1 || nranks > 16 || !flag_slots || !step_dev || !my_flags || !expect_dev || !err)
+            return fail("set_peer_sync: 1..16 flag slots / ranks, counters and an error flag");
+        CU(cudaSetDevice(cfg.device));
+        for (int i = 0; i < n; ++i) sync.slots[i] = flag_slots[i];
+        sync.n = n; sync.nranks = nranks; sync.step_dev = step_dev; sync.my_flags = my_flags; sync.expect_dev = expect_dev;
+        sync.err = err; sync.timeout_us = timeout_us;
+        if (!sync.side) {
+            CU(cudaStreamCreateWithFlags(&sync.side, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&sync.ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sync.ev_join, cudaEventDisableTiming));
+        }
+        sync.set = true;
+        return 0;
+    }
+    int exchange(cudaStream_t st) {
+        if (mpde_peer_exchange_next(sync.slots, sync.n, sync.step_dev, sync.my_flags, sync.nranks, sync.expect_dev, sync.err,
+                                    sync.timeout_us, st))
+            return fail(std::string("step_fused: ") + mpde_peer_last_error());
+        launches += 1;
+        return 0;
+    }
+    int step_fused(const void* actions, int nsub, void* state_out, void* reward_out, int async, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (!peer_bound || !sync.set) return fail("step_fused: bind the gather first (mpde_set_peer_output + mpde_set_peer_sync)");
+        if (nsub <= 0) return fail("step_fused: nsub must be positive (use mpde_step for getState)");
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st) CU(cudaStreamIsCapturing(st, &cs));
+        static const bool use_graph = [] { const char* s = std::getenv("MPDE_HOST_GRAPH"); return !(s && s[0] == '0'); }();
+        if (async) {
+            // publish + wait on the library's side stream, forked behind the step kernel: the caller's stream is free for the
+            // next (independent) batch; mpde_peer_join orders a consumer after the gather.  Capturable by the caller.
+            if (step(actions, nsub, state_out, reward_out, st)) return -1;
+            CU(cudaEventRecord(sync.ev_fork, st));
+            CU(cudaStreamWaitEvent(sync.side, sync.ev_fork, 0));
+            if (exchange(sync.side)) return -1;
+            CU(cudaEventRecord(sync.ev_join, sync.side));
+            sync.pending_join = true;
+            return 0;
+        }
+        if (!use_graph || !st || st == cudaStreamLegacy || cs != cudaStreamCaptureStatusNone) {
+            if (step(actions, nsub, state_out, reward_out, st)) return -1;
+            return exchange(st);
+        }
+        const HostGraph key{actions, state_out, reward_out, nsub, epoch, 0, nullptr, 2, (int)(peer_steps & 1)};
+        int rc = 0;
+        if (find_and_launch(key, st, rc)) return rc;
+        return capture_and_launch(key, st, [&] { return step(actions, nsub, state_out, reward_out, st) ? -1 : exchange(st); });
+    }
+    int peer_join(cudaStream_t st) override {
+        if (sync.pending_join) {
+            CU(cudaStreamWaitEvent(st, sync.ev_join, 0));
+            sync.pending_join = false;
+        }
         return 0;
     }
 
@@ -705,6 +808,16 @@ int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward) {
     if (env) ++env->epoch;
     return env ? env->set_peer_local(local_state, local_reward) : fail("null argument");
 }
+int mpde_set_peer_sync(mpde_env* env, void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
+                       void* expect_dev, void* err, int64_t timeout_us) {
+    if (env) ++env->epoch;
+    return env ? env->set_peer_sync(flag_ptrs, n, step_dev, my_flags_dev, nranks, expect_dev, err, timeout_us) : fail("null argument");
+}
+int mpde_step_fused(mpde_env* env, const void* actions, int32_t nsub, void* state_out, void* reward_out, int32_t async_gather,
+                    void* stream) {
+    return env ? env->step_fused(actions, nsub, state_out, reward_out, async_gather, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
+int mpde_peer_join(mpde_env* env, void* stream) { return env ? env->peer_join(static_cast<cudaStream_t>(stream)) : fail("null argument"); }
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }

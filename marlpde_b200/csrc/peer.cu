@@ -6,6 +6,7 @@
 // shared between the one-process-per-GPU ranks of a node through CUDA IPC handles.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -46,19 +47,39 @@ __global__ void peer_put_kernel(const int4* __restrict__ src, size_t n16, PeerTa
     }
 }
 
-__global__ void peer_wait_kernel(const long long* flags, int nranks, long long step, int* err, long long max_spins) {
-    const int r = threadIdx.x;
-    if (r < nranks) {
-        const volatile long long* f = flags + r;
-        long long spins = 0;
-        while (*f < step) {
-            if (++spins > max_spins) {            // bounded: a missing peer becomes an error flag, never a hang
-                atomicExch(err, 1 + r);
-                break;
-            }
-            __nanosleep(64);
+// Waits are bounded in TIME (%globaltimer), not in polls: a peer that does not publish within `timeout_ns` sets
+// *err = 1 + its rank.  A timed-out wait does NOT advance the expected step, and once *err is set every later wait
+// returns at once, so a dead peer costs one timeout, not one per step; the host sees *err (mapped pinned memory,
+// mpde_host_flag_alloc) on its next call and raises.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// returns true when slot r reached `want`
+__device__ __forceinline__ bool spin_until(const long long* flags, int r, long long want, volatile int* err, long long timeout_ns) {
+    const volatile long long* f = flags + r;
+    if (*f >= want) return true;
+    const unsigned long long t0 = global_ns();
+    long long next_err_poll = 1000000;            // *err may live in mapped host memory: poll it once per millisecond only
+    while (*f < want) {
+        const long long waited = (long long)(global_ns() - t0);
+        if (waited > next_err_poll) {
+            if (*err) return false;               // an earlier wait already timed out: do not wait again
+            next_err_poll += 1000000;
         }
+        if (waited > timeout_ns) {
+            if (*err == 0) *err = 1 + r;          // plain store: *err may be mapped host memory (any timed-out rank will do)
+            return false;
+        }
+        __nanosleep(64);
     }
+    return true;
+}
+
+__global__ void peer_wait_kernel(const long long* flags, int nranks, long long step, int* err, long long timeout_ns) {
+    const int r = threadIdx.x;
+    if (r < nranks) spin_until(flags, r, step, err, timeout_ns);
     __threadfence_system();
 }
 // producer side of the fused gather: runs BEHIND the step kernel in stream order (the kernel boundary makes the step
@@ -74,53 +95,47 @@ __global__ void peer_signal_next_kernel(FlagTable tab, int n, long long* step) {
     }
 }
 // consumer side of the fused gather: the expected step lives on the device (CUDA-graph replayable)
-__global__ void peer_wait_next_kernel(const long long* flags, int nranks, long long* expect, int* err, long long max_spins) {
+__global__ void peer_wait_next_kernel(const long long* flags, int nranks, long long* expect, int* err, long long timeout_ns) {
     __shared__ long long want;
-    if (threadIdx.x == 0) want = *expect + 1;
+    __shared__ int ok;
+    if (threadIdx.x == 0) { want = *expect + 1; ok = 1; }
     __syncthreads();
     const int r = threadIdx.x;
-    if (r < nranks) {
-        const volatile long long* f = flags + r;
-        long long spins = 0;
-        while (*f < want) {
-            if (++spins > max_spins) {
-                atomicExch(err, 1 + r);
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
+    if (r < nranks && !spin_until(flags, r, want, err, timeout_ns)) ok = 0;
     __syncthreads();
-    if (threadIdx.x == 0) *expect = want;
+    if (threadIdx.x == 0 && ok) *expect = want;
     __threadfence_system();
 }
 // signal + wait in one launch (what a symmetric learner loop does after every step)
 __global__ void peer_exchange_next_kernel(FlagTable tab, int n, long long* step, const long long* flags, int nranks, long long* expect,
-                                          int* err, long long max_spins) {
+                                          int* err, long long timeout_ns) {
     __shared__ long long want;
+    __shared__ int ok;
     if (threadIdx.x == 0) {
         const long long s = *step + 1;
         *step = s;
         __threadfence_system();
         for (int q = 0; q < n; ++q) *reinterpret_cast<volatile long long*>(tab.f[q]) = s;
         want = *expect + 1;
+        ok = 1;
     }
     __syncthreads();
     const int r = threadIdx.x;
-    if (r < nranks) {
-        const volatile long long* f = flags + r;
-        long long spins = 0;
-        while (*f < want) {
-            if (++spins > max_spins) {
-                atomicExch(err, 1 + r);
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
+    if (r < nranks && !spin_until(flags, r, want, err, timeout_ns)) ok = 0;
     __syncthreads();
-    if (threadIdx.x == 0) *expect = want;
+    if (threadIdx.x == 0 && ok) *expect = want;
     __threadfence_system();
+}
+long long timeout_ns_of(int64_t timeout_us) {
+    if (timeout_us <= 0) {                        // default: MPDE_PEER_TIMEOUT_S seconds (30)
+        static const long long dflt = [] {
+            const char* s = std::getenv("MPDE_PEER_TIMEOUT_S");
+            const double v = s ? std::atof(s) : 30.0;
+            return (long long)((v > 0 ? v : 30.0) * 1e9);
+        }();
+        return dflt;
+    }
+    return (long long)timeout_us * 1000;
 }
 }  // namespace
 
@@ -136,6 +151,16 @@ int mpde_peer_alloc(size_t bytes, void** out) {
 }
 int mpde_peer_free(void* p) {
     PCU(cudaFree(p));
+    return 0;
+}
+int mpde_host_flag_alloc(int32_t n_int32, void** out) {
+    if (!out || n_int32 < 1) return pfail("host_flag_alloc: bad argument");
+    PCU(cudaHostAlloc(out, (size_t)n_int32 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(*out, 0, (size_t)n_int32 * sizeof(int));
+    return 0;
+}
+int mpde_host_flag_free(void* p) {
+    PCU(cudaFreeHost(p));
     return 0;
 }
 int mpde_peer_export(void* dev_ptr, void* handle64) {
@@ -174,10 +199,10 @@ int mpde_peer_put(const void* src, size_t nbytes, void* const* dst_ptrs, size_t 
     return 0;
 }
 
-int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err_dev, int64_t max_spins, void* stream) {
+int mpde_peer_wait(const void* my_flags_dev, int32_t nranks, int64_t step, void* err_dev, int64_t timeout_us, void* stream) {
     if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait: 1..16 ranks");
     peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks, (long long)step,
-                                                                      static_cast<int*>(err_dev), (long long)max_spins);
+                                                                      static_cast<int*>(err_dev), timeout_ns_of(timeout_us));
     PCU(cudaGetLastError());
     return 0;
 }
@@ -192,23 +217,23 @@ int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, voi
 }
 
 int mpde_peer_exchange_next(void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
-                            void* expect_dev, void* err_dev, int64_t max_spins, void* stream) {
+                            void* expect_dev, void* err_dev, int64_t timeout_us, void* stream) {
     if (n < 1 || n > MAX_RANKS || nranks < 1 || nranks > MAX_RANKS || !flag_ptrs || !step_dev || !expect_dev)
         return pfail("peer_exchange_next: 1..16 ranks, flag slots and both counters");
     FlagTable tab;
     for (int q = 0; q < n; ++q) tab.f[q] = static_cast<long long*>(flag_ptrs[q]);
     peer_exchange_next_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
         tab, n, static_cast<long long*>(step_dev), static_cast<const long long*>(my_flags_dev), nranks,
-        static_cast<long long*>(expect_dev), static_cast<int*>(err_dev), (long long)max_spins);
+        static_cast<long long*>(expect_dev), static_cast<int*>(err_dev), timeout_ns_of(timeout_us));
     PCU(cudaGetLastError());
     return 0;
 }
 
-int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t max_spins, void* stream) {
+int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err_dev, int64_t timeout_us, void* stream) {
     if (nranks < 1 || nranks > MAX_RANKS) return pfail("peer_wait_next: 1..16 ranks");
     peer_wait_next_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const long long*>(my_flags_dev), nranks,
                                                                            static_cast<long long*>(expect_dev),
-                                                                           static_cast<int*>(err_dev), (long long)max_spins);
+                                                                           static_cast<int*>(err_dev), timeout_ns_of(timeout_us));
     PCU(cudaGetLastError());
     return 0;
 }

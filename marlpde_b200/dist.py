@@ -76,7 +76,7 @@ class PeerGather:
     consumer side and ``current()`` the [world_size, chunk_elems] copy the last step wrote (double-buffered).
     """
 
-    def __init__(self, chunk_elems, dtype, device, max_spins=1 << 24, copies=1, backend="auto"):
+    def __init__(self, chunk_elems, dtype, device, timeout_s=None, copies=1, backend="auto"):
         import ctypes as C
         from . import _lib as LB
         self._C, self._lib = C, LB.lib()
@@ -84,7 +84,9 @@ class PeerGather:
         self.device = torch.device(device)
         item = torch.empty((), dtype=dtype).element_size()
         self.chunk_bytes = (chunk_elems * item + 15) // 16 * 16
-        self.chunk_elems, self.dtype, self.max_spins = chunk_elems, dtype, int(max_spins)
+        self.chunk_elems, self.dtype = chunk_elems, dtype
+        # waits are bounded in time: None -> MPDE_PEER_TIMEOUT_S (30 s); a timed-out wait raises on the next host call
+        self.timeout_us = 0 if timeout_s is None else max(1, int(float(timeout_s) * 1e6))
         self.copies = int(copies)
         self._copy_bytes = self.ws * self.chunk_bytes
         gbytes = self.copies * self._copy_bytes
@@ -150,7 +152,11 @@ class PeerGather:
         self._steps_dev = torch.zeros(4, dtype=torch.int64, device=self.device)    # [0] published, [1] awaited
         self._fused = None
         self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self._err = torch.zeros(4, dtype=torch.int32, device=self.device)
+        # error flag in mapped pinned host memory: the wait kernels write it, the host polls it without synchronising
+        ep = C.c_void_p()
+        self._check(self._lib.mpde_host_flag_alloc(4, C.byref(ep)))
+        self._err_ptr = ep.value
+        self._err_host = (C.c_int32 * 4).from_address(ep.value)
         self.step = 0
         if self.ws > 1:
             dist.barrier()
@@ -163,14 +169,19 @@ class PeerGather:
         return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def put(self, src):
+        """Store this rank's slab into every rank's buffer and publish the step.  With ``copies=2`` step s lands in copy
+        (s - 1) & 1, so a fast rank's next put never overwrites rows a slower rank's learner is still reading (a rank
+        can be at most one step ahead: its wait() needs every peer's flag of the previous step)."""
         assert src.is_cuda and src.is_contiguous() and src.numel() * src.element_size() <= self.chunk_bytes
+        self.poll()
         self.step += 1
         nbytes = (src.numel() * src.element_size() + 15) // 16 * 16
-        self._check(self._lib.mpde_peer_put(src.data_ptr(), nbytes, self._dst, self.rank * self.chunk_bytes, self._flags,
+        off = ((self.step - 1) & 1) * self._copy_bytes if self.copies == 2 else 0
+        self._check(self._lib.mpde_peer_put(src.data_ptr(), nbytes, self._dst, off + self.rank * self.chunk_bytes, self._flags,
                                             self.rank, self.ws, self.step, self._counter.data_ptr(), self._stream()))
 
     def wait(self):
-        self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err.data_ptr(), self.max_spins,
+        self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err_ptr, self.timeout_us,
                                              self._stream()))
 
     def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True):
@@ -207,7 +218,13 @@ class PeerGather:
         rc = self._lib.mpde_set_peer_local(env._h, base, base + n_local * S * self._item)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
+        # publish / wait side of the fused step (mpde_step_fused: kernel -> publish -> wait as one host call)
+        rc = self._lib.mpde_set_peer_sync(env._h, self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._my_flags, self.ws,
+                                          self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         env._peer_host_ok = True
+        env._peer_gather = self
         self._fused = env
         env._state_at = env._reward_at = -1
 
@@ -218,28 +235,37 @@ class PeerGather:
     def exchange_next(self):
         """signal_next() + wait_next() as one kernel launch."""
         self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._my_flags, self.ws,
-                                                      self._steps_dev[1:].data_ptr(), self._err.data_ptr(), self.max_spins,
+                                                      self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us,
                                                       self._stream()))
 
     def wait_next(self):
         """Current stream waits until every rank has published one more step than the last wait_next() saw."""
-        self._check(self._lib.mpde_peer_wait_next(self._my_flags, self.ws, self._steps_dev[1:].data_ptr(), self._err.data_ptr(),
-                                                  self.max_spins, self._stream()))
+        self._check(self._lib.mpde_peer_wait_next(self._my_flags, self.ws, self._steps_dev[1:].data_ptr(), self._err_ptr,
+                                                  self.timeout_us, self._stream()))
 
     def current(self):
         """[world_size, chunk_elems] copy written by step number ``self.step`` (1-based host count of fused steps)."""
         return self._all[(self.step - 1) & 1] if self.copies == 2 else self._all[0]
 
-    def check(self):
-        e = int(self._err[0])
+    def poll(self):
+        """Raise if a wait kernel has timed out so far (reads the mapped host flag: no synchronisation, ~50 ns)."""
+        e = int(self._err_host[0])
         if e:
-            raise RuntimeError(f"peer gather timed out waiting for rank {e - 1}")
+            raise RuntimeError(f"peer gather timed out waiting for rank {e - 1}: the gathered rows are stale "
+                               f"(timeout {self.timeout_us / 1e6 if self.timeout_us else 'MPDE_PEER_TIMEOUT_S'} s)")
+
+    def check(self):
+        """poll() after draining the device: the definitive answer for everything enqueued so far."""
+        torch.cuda.synchronize(self.device)
+        self.poll()
 
     def close(self):
         if getattr(self, "_base", None):
             torch.cuda.synchronize(self.device)
             if self._fused is not None:
                 self._lib.mpde_set_peer_output(self._fused._h, 0, None, None, 0, None, None)
+                self._lib.mpde_set_peer_sync(self._fused._h, None, 0, None, None, 0, None, None, 0)
+                self._fused._peer_gather = None
                 self._fused = None
             if self.ws > 1:
                 dist.barrier()
@@ -249,6 +275,10 @@ class PeerGather:
                 self._lib.mpde_peer_free(self._base)
             self._symm = None
             self._base = None
+            if self._err_ptr:
+                self._err_host = None
+                self._lib.mpde_host_flag_free(self._err_ptr)
+                self._err_ptr = None
 
 
 class ShardedBatch:
@@ -281,7 +311,7 @@ class ShardedBatch:
                 self._peer.fuse(self.env, nl, S, A)
                 self._gflat = self._peer.gathered
             elif transport == "p2p":
-                self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device)
+                self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device, copies=2)
                 self._gflat = self._peer.gathered
             else:
                 self._peer = None
@@ -307,7 +337,9 @@ class ShardedBatch:
     def views(self):
         """(states [R, B/R, S], rewards [R, B/R, A]) views of the gathered buffer, global env order."""
         nl = self.hi - self.lo
-        g = self._peer.current() if self.transport == "fused" else self._gflat
+        if self._peer is not None:
+            self._peer.poll()                         # a timed-out gather raises here instead of handing out stale rows
+        g = self._peer.current() if self._peer is not None else self._gflat
         return g[:, :nl * self._S].view(self.world_size, nl, self._S), g[:, nl * self._S:].view(self.world_size, nl, self._A)
 
     def step_n(self, actions_global_or_local, n=1, async_gather=False, **kw):
@@ -315,6 +347,14 @@ class ShardedBatch:
         if a is not None and len(a) == self.n_global and self.world_size > 1:
             a = a[self.lo:self.hi]
         self.wait()                                   # the send buffer is about to be overwritten
+        if self.transport == "fused" and self._flat is not None and not kw and self.env._reward_enabled():
+            # ONE library call: step kernel (rows stored straight into every rank's buffer) -> publish -> wait, replayed
+            # from a CUDA graph cached per parity (mpde_step_fused)
+            self._peer.poll()
+            self.env.step_n_fused(a, n, async_gather=async_gather)
+            self._peer.step += 1
+            gs, gr = self.views()
+            return gs.reshape(self.n_global, self._S), gr.reshape(self.n_global, self._A)
         st, rw = self.env.step_n(a, n, **kw)
         if self._flat is not None and st is not None and rw is not None:
             if self.transport == "fused":

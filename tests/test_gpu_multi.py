@@ -206,3 +206,74 @@ def test_host_pipeline_with_fused_gather_single_rank():
         cur = sb._peer.current()[0]
         assert torch.equal(cur[:B * S].view(B, S), st) and torch.equal(cur[B * S:].view(B, 1), rw), k
     sb._peer.close()
+
+
+def test_peer_wait_timeout_is_reported_not_silent():
+    """a peer that never publishes must surface as an error.  The wait is bounded in time, does not advance the
+    expected step, later waits give up quickly, and the host sees the flag without synchronising (mapped pinned memory)."""
+    import time
+    from marlpde_b200.dist import PeerGather
+    torch.cuda.set_device(0)
+    pg = PeerGather(64, torch.float64, "cuda:0", timeout_s=0.05, copies=2)
+    pg.poll()
+    pg.wait_next()                          # nobody published step 1
+    torch.cuda.synchronize()
+    assert int(pg._steps_dev[1]) == 0       # expected step NOT advanced
+    with pytest.raises(RuntimeError, match="timed out waiting for rank 0"):
+        pg.poll()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pg.wait_next()
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.2   # 5 further waits cost ~1 ms each, not 5 timeouts
+    with pytest.raises(RuntimeError):
+        pg.check()
+    pg.close()
+
+
+def test_fused_gather_keeps_getstate_and_reset_working():
+    """with a fused gather bound, nsub == 0 calls (getState at episode reset) write the local buffers only and
+    do not flip the parity of the gather copies; multi-episode loops therefore run in fused mode."""
+    from marlpde_b200 import dist as mdist
+    torch.cuda.set_device(0)
+    sb = mdist.ShardedBatch(B, _factory, transport="fused")
+    ref = _factory(B, np.arange(B))
+    a = _acts().cuda()
+    for episode in range(2):
+        sb.env.IC(case="turbulence")
+        ref.IC(case="turbulence")
+        s0 = sb.env.getState()
+        assert torch.equal(s0, ref.getState())
+        for k in range(3):                  # odd number of steps: the next episode starts on the other parity
+            gs, gr = sb.step_n(a, 5)
+            st, rw = ref.step_n(a, 5)
+            torch.cuda.synchronize()
+            assert torch.equal(gs, st) and torch.equal(gr, rw), (episode, k)
+    sb._peer.check()
+    sb._peer.close()
+
+
+def test_failed_fused_step_does_not_flip_parity():
+    """A step that cannot launch (spectral reward without a reference) must leave the parity counter alone."""
+    from marlpde_b200 import Burger, dist as mdist
+    from marlpde_b200.dist import PeerGather
+    torch.cuda.set_device(0)
+    env = Burger(N=N, dt=1e-3, nu=0.02, tend=1.0, case="turbulence", forcing=False, dforce=False, seed=50, nenvs=B, history=False)
+    env.setup_basis(M, "hat")
+    S = env._state_buf.shape[1]
+    pg = PeerGather(B * (S + 1), torch.float64, "cuda:0", copies=2)
+    pg.fuse(env, B, S, 1)
+    env._lib.mpde_set_reward_mode(env._h, 1)                 # spectral reward, but no reference table bound
+    a = _acts().cuda()
+    with pytest.raises(RuntimeError, match="spectral reward without"):
+        env.step_n_fused(a, 5)
+    ref = np.abs(np.random.default_rng(0).normal(1.0, 0.1, (1001, N // 2))) * 1e-3 + 1e-6
+    env.set_spectrum_reference(ref)
+    env.step_n_fused(a, 5)
+    pg.step += 1
+    torch.cuda.synchronize()
+    # the first successful step wrote copy 0
+    cur = pg.current()[0]
+    assert torch.isfinite(cur).all() and float(cur[:B * S].abs().max()) > 0
+    assert float(pg._all[1].abs().max()) == 0.0
+    pg.close()

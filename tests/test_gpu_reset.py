@@ -104,3 +104,48 @@ def test_spline_table_on_device_matches_fitpack():
     _, ra = a.step_n(acts, 5)
     _, rb = b.step_n(acts, 5)
     assert rel(ra, rb.cpu().numpy()) < 1e-10
+
+
+@pytest.mark.parametrize("nsteps,stepper,nunoise,nseeds", [(1000, 1, False, 4096), (5000, 1, False, 48), (777, 4, True, 96), (300, 20, True, 33)])
+def test_device_forcing_tables_match_numpy_stream(nsteps, stepper, nunoise, nseeds):
+    """SURVEY 8f-1 / Burger.py:66,88-95: the device generator (one warp per seed: MT19937 init_genrand, 53-bit doubles,
+    legacy polar gauss) reproduces rows 1..3, columns < stepper of `np.random.seed(seed); [uniform();] normal(size=(32,nsteps)) x 2`.
+    Acceptance of the polar candidates is exact arithmetic (identical stream position); the kept value goes through log(),
+    whose last bit differs between CUDA and glibc: <= 2 ulp allowed, and most entries must be bit-equal."""
+    from marlpde_b200.Burger import device_forcing_tables
+    seeds = 42 + np.arange(nseeds)
+    nu, r1, r2 = device_forcing_tables(seeds, nsteps, stepper, nunoise, "cuda:0")
+    e1, e2, en = np.empty_like(r1), np.empty_like(r2), np.empty(nseeds)
+    for i, sd in enumerate(seeds):
+        rs = np.random.RandomState(int(sd))
+        if nunoise:
+            en[i] = 0.01 + 0.02 * rs.uniform()
+        e1[i] = rs.normal(loc=0., scale=1., size=(32, nsteps))[1:4, :stepper]
+        e2[i] = rs.normal(loc=0., scale=1., size=(32, nsteps))[1:4, :stepper]
+    if nunoise:
+        assert np.array_equal(nu, en)
+    for got, exp in ((r1, e1), (r2, e2)):
+        assert np.all(np.abs(got - exp) <= 2 * np.spacing(np.abs(exp)))
+        assert np.mean(got == exp) > 0.8
+
+
+def test_burger_batch_with_per_env_seeds_uses_device_tables_and_matches_single_envs():
+    """bench workload: seed = 42 + e per environment.  The batch built from device-generated tables steps
+    like single environments built from the host NumPy stream (1e-12: the table entries agree to <= 2 ulp)."""
+    from marlpde_b200 import Burger
+    B, N, M = 64, 32, 32
+    seeds = 42 + np.arange(B)
+    kw = dict(N=N, dt=1e-3, nu=0.02, tend=0.2, case="turbulence", forcing=True, dforce=False, history=False)
+    env = Burger(seed=seeds, nenvs=B, **kw)
+    assert env._tables_on_device
+    env.setup_basis(M, "hat")
+    a = np.random.default_rng(0).uniform(0.0, 0.05, (B, M))
+    env.step_n(a, 20)
+    u = env.u.cpu().numpy()
+    for e in (0, 17, 63):
+        one = Burger(seed=int(seeds[e]), nenvs=1, **kw)
+        assert not one._tables_on_device
+        one.setup_basis(M, "hat")
+        one.step_n(a[e:e + 1], 20)
+        ref = one.u.cpu().numpy()
+        assert np.max(np.abs(u[e] - ref)) <= 1e-12 * np.max(np.abs(ref))
