@@ -309,7 +309,10 @@ def gpu_arm(args):
     pool = max(1, args.pool)
     make = make_batch_c5 if args.workload == "c5" else make_batch
     B = 8192 if args.workload == "c5" else B_PER_GPU
-    envs = [make(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
+    if args.workload == "c5":
+        envs = [make(torch, device, 42 + 16 * i + 1000 * rank) for i in range(pool)]
+    else:
+        envs = [make(torch, device, 42 + 16 * i + 1000 * rank, team_lanes=args.lanes) for i in range(pool)]
     rng = np.random.default_rng(rank)
     # eddy-viscosity coefficients: one value per (environment, action), positive (a stabilising closure)
     acts_host = torch.from_numpy(rng.uniform(0.02, 0.1, (pool, B, M))).pin_memory()
@@ -369,6 +372,8 @@ def gpu_arm(args):
         return g_, n_k
 
     chains = max(1, min(args.chains, pool))
+    if pool % chains:
+        chains = 1                          # a batch must stay on one chain (its launches are ordered by its stream)
     # every batch once outside any graph (module load, lazy set-up, first-use allocations)
     for i in range(pool):
         one_step(i)
@@ -565,7 +570,7 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": facts.get("traffic_bytes_per_launch", {}).get("c5" if args.workload == "c5" else "c2"),
                          "traffic_source": facts.get("traffic_source"), "peak_source": how,
-                         "kernel": "burgers_warp_kernel<double,32,8,FORCING|ACTIONS,HOT>" if args.workload != "c5"
+                         "kernel": "burgers_warp_kernel<double,32,4,FORCING|ACTIONS,HOT>" if args.workload != "c5"
                                    else "burgers_warp_kernel<double,32,4,generic>",
                          "bytes_per_launch": B * bytes_env,
                          "launch_us": per_launch_s * 1e6,
@@ -611,7 +616,7 @@ def batch_sweep(torch, device):
     fp64_peak = float(kernel_facts().get("fp64_peak_tflops", 33.2))
     out = []
     spec = spectrum_table()
-    for B, nsub, lanes in ((4096, 10, 8), (8192, 10, 4), (32768, 10, 4), (32768, 1, 4), (131072, 1, 4)):
+    for B, nsub, lanes in ((4096, 10, 4), (4096, 10, 8), (8192, 10, 4), (32768, 10, 4), (32768, 1, 4), (131072, 1, 4)):
         per_batch = B * 1912
         pool = max(2, -(-160_000_000 // per_batch))
         envs = [make_batch(torch, device, 7 + i, B=B, team_lanes=lanes, spec=spec) for i in range(pool)]
@@ -718,7 +723,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the sweep / other-config / single-chain extras")
     ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")
-    ap.add_argument("--chains", type=int, default=2, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--chains", type=int, default=4, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per environment (0 = library default)")
     ap.add_argument("--rewards-only", action="store_true", help="multi-GPU: gather only the rewards (configs[4] wording)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")
     args = ap.parse_args()

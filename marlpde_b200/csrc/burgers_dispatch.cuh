@@ -91,10 +91,11 @@ int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
     template int launch_burgers_##N_##_##NAME_<float>(const SpectralParams<float>&, cudaStream_t);
 #define MPDE_INSTANTIATE_TEAM(N_, TS_) MPDE_INSTANTIATE_TEAM_AS(N_, TS_, TS_)
 
-// Team size = lanes per environment: a function of N ONLY by default (two complex points per lane: N = 32 -> 8 lanes,
-// N = 64 -> 16 lanes), never of the batch size, because the variants round differently and environment e must give the
-// same bits alone or inside a batch of 65536.  B200, fp64 N = 32, 10 fused sub-steps, us per launch:
-//   B = 4096: 16 lanes 14.8, 8 lanes 13.4, 4 lanes 13.9;  B = 8192: 24.2 / 25.7 / 19.5;  B = 32768: 86.6 / 89.9 / 64.0.
+// Team size = lanes per environment: a function of N ONLY by default (N = 32 -> 4 lanes, N = 64 -> 16 lanes), never of the
+// batch size, because the variants round differently and environment e must give the same bits alone or inside a batch
+// of 65536.  B200, fp64 N = 32, 10 fused sub-steps, us per launch, one batch at a time:
+//   B = 4096: 16 lanes 14.8, 8 lanes 13.4, 4 lanes 13.9;  B = 8192: 24.2 / 25.7 / 19.5;  B = 32768: 86.6 / 89.9 / 64.0;
+// B = 4096 with 4 independent batches in flight (round 2): 16 lanes 10.1, 8 lanes 10.4, 4 lanes 7.2.
 // mpde_config.team_lanes (Burger(team_lanes=...)) or MPDE_TS (whole process) select a variant:
 //   4 / 8 / 16 : that many lanes;
 //   -8         : 8 lanes with the radix-2^2 shuffle network whose arithmetic is bit-identical to the 4-lane kernel
@@ -108,7 +109,10 @@ inline int pick_team(int requested, int64_t B, int N, int flags, int ts_max, int
     if (N == 32 && requested == -1) return (B >= 6144 && !(flags & F_DSM)) ? 4 : -8;
     if (N == 32 && requested == -8) return -8;
     if (requested >= ts_min && requested <= ts_max && (requested & (requested - 1)) == 0) return requested;
-    const int ts = N / 4;           // P = (N/2) / ts = 2 complex points per lane
+    // default: N = 32 -> 4 lanes per environment (the 4 x 4 shared-memory-transposed transform: fewest instructions per
+    // environment; with several independent batches in flight it is also the fastest at B = 4096: 7.2 us per launch
+    // against 10.4 us with 8 lanes, profiles/r2_lanes_chains.md); other N -> two complex points per lane
+    const int ts = N == 32 ? 4 : N / 4;
     return ts > ts_max ? ts_max : (ts < ts_min ? ts_min : ts);
 }
 

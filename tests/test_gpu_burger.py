@@ -224,6 +224,26 @@ def test_full_size_config2_properties():
     from marlpde_b200 import _lib as LB
     kprev = env._get(LB.FIELD_KPREV, (B,), torch.float64)
     assert torch.allclose(tot[:, 0], -kprev, rtol=1e-9, atol=1e-12)
+    # sampled rows of the full-size run (the HOT kernel variant the bench times) against the oracle, 1e-10
+    from oracle.burger_oracle import BurgerOracle, forcing_tables, turbulence_ic
+    from oracle.common import grid, spectral_rel_err
+    rows = np.array([0, 1, 777, 1024, 2047, 2048, 3333, 4095])
+    o = BurgerOracle(B=len(rows), L=TWO_PI, N=N, dt=1e-3, nu=0.02, forcing=True, dforce=False)
+    o.setup_basis(32, "hat")
+    tabs = [forcing_tables(int(s_), 5000) for s_ in seeds[rows]]
+    o.set_forcing_tables(np.stack([t[0][:, :1] for t in tabs]), np.stack([t[1][:, :1] for t in tabs]))
+    o.IC(u0=np.stack([turbulence_ic(grid(TWO_PI, N), TWO_PI, N, 0.0, int(s_)) for s_ in seeds[rows]]))
+    prev = np.zeros(len(rows))
+    for _ in range(3):
+        for _ in range(10):
+            o.step(acts[rows])
+        err = np.array([spectral_rel_err(ref[o.ioutnum], o.Ek_ktt_row()[i], N) for i in range(len(rows))])
+        o_rw, prev = prev - err, err
+    u_gpu = env.u.cpu().numpy()[rows]
+    assert np.max(np.abs(u_gpu - o.u)) <= 1e-10 * np.max(np.abs(o.u))
+    assert np.max(np.abs(env.v.cpu().numpy()[rows] - o.v)) <= 1e-10 * np.max(np.abs(o.v))
+    assert np.max(np.abs(st.cpu().numpy()[rows] - o.state())) <= 1e-9 * np.max(np.abs(o.state()))
+    np.testing.assert_allclose(rw.cpu().numpy()[rows, 0], o_rw, rtol=1e-5, atol=1e-9)
 
 
 def test_host_buffer_step_equals_device_step(golden):
