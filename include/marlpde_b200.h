@@ -33,7 +33,13 @@ extern "C" {
 
 #define MPDE_ABI_VERSION 1
 
-enum mpde_equation { MPDE_BURGERS = 0, MPDE_KS = 1, MPDE_DIFFUSION = 2, MPDE_ADVECTION = 3 };
+enum mpde_equation {
+    MPDE_BURGERS = 0, MPDE_KS = 1, MPDE_DIFFUSION = 2, MPDE_ADVECTION = 3,
+    MPDE_DIFFUSION_ERROR = 4, /* DiffusionError.py:160-216: the action is the ERROR of the Laplacian stencil            */
+    MPDE_LAPLACE = 5          /* Laplace.py:116-166: N grid points incl. the Dirichlet point 0 (the class's N + 1), 3 free */
+                              /* stencil entries per agent (M = 3 (N - 1)), forcing row via mpde_set_truth ([.,1,N]),    */
+                              /* state [u_{i-1}, u_i, u_{i+1}, force_i] (4 (N - 1)), reward MPDE_REWARD_DIRECT (N - 1)    */
+};
 enum mpde_dtype { MPDE_F64 = 0, MPDE_F32 = 1 };
 enum mpde_status { MPDE_RUNNING = 0, MPDE_TRUNCATED = 1 };
 enum mpde_reward { MPDE_REWARD_NONE = 0, MPDE_REWARD_SPECTRAL = 1, MPDE_REWARD_MSE = 2, MPDE_REWARD_DIRECT = 3 };
@@ -45,7 +51,7 @@ enum mpde_reward { MPDE_REWARD_NONE = 0, MPDE_REWARD_SPECTRAL = 1, MPDE_REWARD_M
 #define MPDE_DSM      (1 << 3) /* Burger(dsm=True): dynamic Smagorinsky closure                  */
 #define MPDE_IMPLICIT (1 << 4) /* Diffusion(implicit=True): implicit-Euler FDstep                */
 #define MPDE_FD       (1 << 5) /* Burger_fd: explicit Euler + finite differences (Burger_fd.py:335-476);  */
-                               /* warp-resident kernels only (N <= 256), state versions 0 and 2, no dsm  */
+                               /* warp-resident kernels only (N <= 256), state versions 0, 1 and 2       */
 #define MPDE_SSMFORCE (1 << 6) /* Burger_fd(ssmforce=True): actions are Smagorinsky coefficients          */
 
 /* fields for mpde_get / mpde_set */
@@ -196,6 +202,13 @@ int mpde_step_host(mpde_env* env, const void* actions_host, int32_t nsub, void* 
  * single D2H copy, which is worth ~30 % of the end-to-end rate at B = 4096 (one DMA operation per direction per step).
  * The reward part is written when a reward mode is set and nsub > 0. */
 int mpde_step_host_packed(mpde_env* env, const void* actions_host, int32_t nsub, void* out_host, void* stream);
+
+/* A-priori sub-grid-scale term of the recorded history, Burger.compute_Sgs(nURG) (Burger.py:677-736) / KS.compute_Sgs
+ * (KS.py:385-409): for every row of the uu history bound with mpde_set_history (rows = its length), filter u and u^2 with the
+ * sharp cut |k| > nURG // 2 and write  sgs_out [B, rows, N] = -uh duh/dx + 0.5 d(u^2)h/dx  and, for Burgers (NULL to skip),
+ * alt_out [B, rows, N] = duh/dt + uh duh/dx - nu d2uh/dx2 and alt2_out [B, rows, nURG] (the same on the nURG-point grid of the
+ * truncated spectrum).  N in {256, 512, 1024, 2048}, nURG <= 64.  Evaluation-time diagnostic (testing mode), not a hot path. */
+int mpde_compute_sgs(mpde_env* env, int32_t nURG, int64_t rows, void* sgs_out, void* alt_out, void* alt2_out, void* stream);
 
 /* attribute access (u, v, Fn_old, ioutnum, t, ...): DEVICE destination / source of the natural shape */
 int mpde_get(mpde_env* env, int32_t field, void* dst_dev, void* stream);

@@ -334,3 +334,157 @@ class Advection(_FDEnv):
 
 def _np(a):
     return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
+class DiffusionError(Diffusion):
+    """Diffusion whose actions are the ERROR of the Laplacian stencil: row k of the update matrix is
+    (1 - a_k/2, -2 + a_k, 1 - a_k/2) (/root/reference/python/_model/DiffusionError.py:160-216).  Same constructor, IC cases,
+    state and rewards as ``Diffusion``; only ``step(actions, numAgents)`` differs (in the kernel: fd_launch.cu)."""
+    equation = LB.DIFFUSION_ERROR
+    name = "Diffusion"          # the reference keeps the [Diffusion] prefix in its messages
+
+
+class Laplace(BatchedEnv):
+    """Relaxation towards u_xx = f on N + 1 points with one Dirichlet point u[0] = 1; agent i owns row i + 1 of the update
+    matrix and sets its three entries (/root/reference/python/_model/Laplace.py:8-166).  ``step(actions, numAgents)`` with
+    ``numAgents == N`` (the class's N, i.e. constructor N + 1 points minus the boundary point) and three actions per agent;
+    ``getState`` -> [u_{i-1}, u_i, u_{i+1}, force_i] per agent, ``getDirectReward`` -> -(u_xx - force)^2 on points 1..N."""
+    equation = LB.LAPLACE
+
+    def __init__(self, L=2. * np.pi, N=512, dt=0.01, ic='one', sforce='zero', episodeLength=100, noise=0., version=0, *,
+                 nenvs=1, device=None, dtype=torch.float64, history=None, offset=None, force_seed=None):
+        B = int(nenvs)
+        self.N = int(N) + 1                                              # Laplace.py:18
+        self.L, self.dt = float(L), float(dt)
+        self.nsteps = self.nout = int(episodeLength)
+        rng = np.random.default_rng(force_seed)                         # the reference draws from the unseeded global stream
+        self._rng = rng
+        if offset is not None:
+            self._offset = np.broadcast_to(np.asarray(offset, dtype=np.float64), (B,)).copy()
+        else:
+            self._offset = rng.normal(0., self.L * noise, B) if noise > 0. else np.zeros(B)
+        self.version = version
+        self.dx = L / self.N
+        self.x = np.linspace(0, self.L, self.N, endpoint=False)
+        self._create(nenvs=B, N=self.N, L_=self.L, dt=self.dt, M=3 * (self.N - 1), num_agents=1, version=0, stepper=1,
+                     flags=0, reward_mode=LB.REWARD_DIRECT, device=device, dtype=dtype)
+        L_check(self._lib.mpde_set_nu(self._h, LB.as_dp(np.zeros(B)), B))
+        rows = self.nout + 1
+        if history is None:
+            history = B * rows * self.N * 8 <= (2 << 30)
+        self.history = bool(history)
+        self.tt = np.concatenate(([0.], np.cumsum(np.full(self.nout, self.dt))))
+        if self.history:
+            self._uu = torch.zeros((B, rows, self.N), device=self.device, dtype=self.dtype)
+            L_check(self._lib.mpde_set_history(self._h, self._ptr(self._uu), None, None, rows))
+        self.ic, self.sforce = ic, sforce
+        self.IC(ic=ic, sforce=sforce)
+
+    @property
+    def offset(self):
+        return float(self._offset[0]) if self.nenvs == 1 else self._offset
+
+    def _squeeze(self, t):
+        return t[0] if self.nenvs == 1 else t
+
+    @property
+    def u(self):
+        return self._squeeze(self._get(LB.FIELD_U, (self.nenvs, self.N), self.dtype))
+
+    @property
+    def uu(self):
+        if not self.history:
+            raise RuntimeError("history recording is off for this batch (pass history=True)")
+        return self._squeeze(self._uu)
+
+    def IC(self, ic='one', sforce='zero'):
+        """Laplace.py:46-114."""
+        B, x, L = self.nenvs, self.x[None, :], self.L
+        off = self._offset[:, None]
+        if ic == 'zero':
+            u0 = np.zeros((B, self.N))
+        elif ic == 'one':
+            u0 = np.ones((B, self.N))
+        elif ic == 'sin':
+            u0 = np.broadcast_to(1. + np.sin(x), (B, self.N)).copy()
+        elif ic == 'cos':
+            u0 = np.broadcast_to(np.cos(x), (B, self.N)).copy()
+        else:
+            raise SystemExit("[Laplace] Error: ic unknown")
+        sin1, cos1 = np.sin((x - off) * 2 * np.pi / L), np.cos((x - off) * 2 * np.pi / L)
+        if sforce == 'zero':
+            force = np.zeros((B, self.N))
+        elif sforce == 'sin':
+            force = sin1
+        elif sforce == 'cos':
+            force = cos1
+        elif sforce == 'sincos':
+            pick = self._rng.random(B)[:, None] > 0.5
+            force = np.where(pick, sin1, cos1)
+        elif sforce == 'fourier':
+            r = self._rng.random(B)[:, None]
+            force = np.where(r > 0.66, sin1, np.where(r > 0.33, np.sin((x - off) * 3 * np.pi / L), np.sin((x - off) * 4 * np.pi / L)))
+        elif sforce == 'gaussian':
+            force = np.exp(-0.5 * (0.5 * L - x + off) ** 2)
+        else:
+            raise SystemExit(f"[Laplace] Error: force {sforce} unknown")
+        force = np.broadcast_to(force, (B, self.N)).copy()
+        self._u0 = u0
+        u0d = self._batch(u0, self.dtype, (self.N,))
+        L_check(self._lib.mpde_reset_u(self._h, self._ptr(u0d), None, self._stream()))
+        self.u0 = self._squeeze(u0d)
+        self._force = force
+        shared = B == 1 or bool(np.all(force == force[0]))
+        tab = self._dev(force[:1] if shared else force).reshape(-1, 1, self.N).contiguous()
+        mp = None
+        if not shared:
+            self._keep['truth_map'] = self._dev(np.arange(B), torch.int32, (B,))
+            mp = self._ptr(self._keep['truth_map'])
+        self._keep['truth'] = tab
+        L_check(self._lib.mpde_set_truth(self._h, self._ptr(tab), tab.shape[0], 1, mp))
+        L_check(self._lib.mpde_set_reward_mode(self._h, LB.REWARD_DIRECT))
+        self.t, self.stepnum, self.ioutnum = 0., 0, 0
+
+    @property
+    def force(self):
+        return self._force[0] if self.nenvs == 1 else self._force
+
+    def step_n(self, actions, numAgents, n=1, want_state=False, want_reward=False):
+        assert numAgents + 1 == self.N                                    # Laplace.py:118 (one boundary point)
+        if isinstance(actions, torch.Tensor):
+            a = actions.to(device=self.device, dtype=self.dtype)
+        else:
+            a = torch.as_tensor(np.asarray(actions, dtype=np.float64), device=self.device).to(self.dtype)
+        a = a.reshape(self.nenvs, -1).contiguous()
+        assert a.shape[1] == 3 * numAgents, f"[Laplace] action len not 3, it is {a.shape[1] / numAgents}"
+        nA = numAgents
+        st = torch.empty((self.nenvs, 4 * nA), device=self.device, dtype=self.dtype) if want_state else None
+        rw = torch.empty((self.nenvs, nA), device=self.device, dtype=self.dtype) if want_reward else None
+        L_check(self._lib.mpde_step(self._h, self._ptr(a), int(n), self._ptr(st), self._ptr(rw), self._stream()))
+        self.stepnum += n
+        self.ioutnum += n
+        for _ in range(n):
+            self.t += self.dt
+        return st, rw
+
+    def step(self, actions, numAgents):
+        self.step_n(actions, numAgents, 1)
+
+    def getDirectReward(self, numAgents=1, as_tensor=None):
+        """Laplace.py:153-160."""
+        assert numAgents + 1 == self.N, f"[Laplace] direct reward neeeds N agents (using {numAgents})"
+        rw = torch.empty((self.nenvs, numAgents), device=self.device, dtype=self.dtype)
+        L_check(self._lib.mpde_step(self._h, None, 0, None, self._ptr(rw), self._stream()))
+        if as_tensor is None:
+            as_tensor = self.nenvs > 1
+        return rw if as_tensor else rw[0].cpu().numpy().tolist()
+
+    def getState(self, numAgents=1, as_tensor=None):
+        """Laplace.py:162-166."""
+        assert self.N == numAgents + 1
+        st = torch.empty((self.nenvs, 4 * numAgents), device=self.device, dtype=self.dtype)
+        L_check(self._lib.mpde_step(self._h, None, 0, self._ptr(st), None, self._stream()))
+        st = st.view(self.nenvs, numAgents, 4)
+        if as_tensor is None:
+            as_tensor = self.nenvs > 1
+        return st if as_tensor else st[0].cpu().numpy().tolist()

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmarlpde_b200.so")
 
 # enums (include/marlpde_b200.h)
-BURGERS, KS, DIFFUSION, ADVECTION = 0, 1, 2, 3
+BURGERS, KS, DIFFUSION, ADVECTION, DIFFUSION_ERROR, LAPLACE = 0, 1, 2, 3, 4, 5
 F64, F32 = 0, 1
 RUNNING, TRUNCATED = 0, 1
 REWARD_NONE, REWARD_SPECTRAL, REWARD_MSE, REWARD_DIRECT = 0, 1, 2, 3
@@ -57,6 +57,7 @@ SIGNATURES = {
     "mpde_eval_spline_table": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _vp]),
     "mpde_step_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mpde_step_host_packed": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "mpde_compute_sgs": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "mpde_get": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mpde_set": (C.c_int, [_vp, _i32, _vp, _vp]),
     "mpde_launch_count": (_i64, [_vp]),

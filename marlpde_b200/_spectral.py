@@ -81,6 +81,21 @@ class SpectralEnv(BatchedEnv):
         self._need_history()
         return self._squeeze(self._vv)
 
+    def compute_Sgs(self, nURG):
+        """Burger.py:677-736 / KS.py:385-409: a-priori sub-grid-scale term of the recorded history for a coarse grid of
+        ``nURG`` modes (testing-mode diagnostic).  Sets ``sgsHistory`` [rows, N] and, for Burgers, ``sgsHistoryAlt``
+        [rows, N], ``sgsHistoryAlt2`` [rows, nURG] (device tensors; leading environment axis when nenvs > 1)."""
+        self._need_history()
+        B, rows, N = self.nenvs, self.nout + 1, self.N
+        burgers = self.equation == LB.BURGERS
+        sgs = torch.zeros((B, rows, N), device=self.device, dtype=self.dtype)
+        alt = torch.zeros((B, rows, N), device=self.device, dtype=self.dtype) if burgers else None
+        alt2 = torch.zeros((B, rows, int(nURG)), device=self.device, dtype=self.dtype) if burgers else None
+        L_check(self._lib.mpde_compute_sgs(self._h, int(nURG), rows, self._ptr(sgs), self._ptr(alt), self._ptr(alt2), self._stream()))
+        self.sgsHistory = self._squeeze(sgs)
+        if burgers:
+            self.sgsHistoryAlt, self.sgsHistoryAlt2 = self._squeeze(alt), self._squeeze(alt2)
+
     def _need_history(self):
         if not self.history:
             raise RuntimeError("history recording is off for this batch (pass history=True)")

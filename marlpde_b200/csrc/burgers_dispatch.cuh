@@ -65,7 +65,7 @@ int launch_warp_lean(const SpectralParams<T>& p, cudaStream_t st) {
 }
 template <typename T, int N, int TS>
 int launch_warp_sf(const SpectralParams<T>& p, cudaStream_t st) {
-    if (p.flags & F_FD) return launch_warp<T, N, TS, -1>(p, st);      // Burger_fd lives in the generic kernel only
+    if (p.flags & F_FD) return launch_warp<T, N, TS, -2>(p, st);      // Burger_fd: its own instantiation of the generic kernel
     if constexpr (sizeof(T) == 8) {
         switch (p.flags & STRUCT_FLAGS) {
             case F_ACTIONS: return launch_warp_lean<T, N, TS, F_ACTIONS>(p, st);

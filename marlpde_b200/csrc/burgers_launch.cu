@@ -24,12 +24,12 @@ static int launch_burgers_64(const SpectralParams<T>& p, cudaStream_t st) {
 template <typename T>
 int launch_burgers(const SpectralParams<T>& p, cudaStream_t st) {
     switch (p.N) {
-        case 8: return launch_warp<T, 8, 4, -1>(p, st);
-        case 16: return launch_warp<T, 16, 8, -1>(p, st);
+        case 8: return (p.flags & F_FD) ? launch_warp<T, 8, 4, -2>(p, st) : launch_warp<T, 8, 4, -1>(p, st);
+        case 16: return (p.flags & F_FD) ? launch_warp<T, 16, 8, -2>(p, st) : launch_warp<T, 16, 8, -1>(p, st);
         case 32: return launch_burgers_32<T>(p, st);
         case 64: return launch_burgers_64<T>(p, st);
-        case 128: return launch_warp<T, 128, 32, -1>(p, st);
-        case 256: return launch_warp<T, 256, 32, -1>(p, st);
+        case 128: return (p.flags & F_FD) ? launch_warp<T, 128, 32, -2>(p, st) : launch_warp<T, 128, 32, -1>(p, st);
+        case 256: return (p.flags & F_FD) ? launch_warp<T, 256, 32, -2>(p, st) : launch_warp<T, 256, 32, -1>(p, st);
         default: return launch_burgers_cta<T>(p, st);
     }
 }

@@ -11,7 +11,7 @@
 //     real-FFT, then state / reward / spectrum sums are written back coalesced;
 //   * action forcing, 3-mode stochastic forcing, Smagorinsky closures, the float32
 //     spectrum chain and the spectral / MSE rewards are fused in;
-//   * SF >= 0 fixes the structural mode flags at compile time (hot configurations), SF < 0
+//   * SF >= 0 fixes the structural mode flags at compile time (hot configurations), SF < 0 (-1 generic, -2 Burger_fd)
 //     reads them at run time (generic kernel).
 // No arithmetic of one environment depends on another one: results are bitwise
 // independent of batch size and packing.
@@ -91,6 +91,74 @@ struct BurgersWarp {
     // float64 -> float32 -> float64 (quirk Q1: the forcing accumulator of the reference is
     // complex64 unless the stochastic forcing replaced it, Burger.py:335,466)
     __device__ __forceinline__ static T r32(T a) { return (T)(float)a; }
+
+    // Dynamic Smagorinsky closure (Burger.py:357-399 = Burger_fd.py:358-411): Germano identity with a sharp spectral test
+    // filter |k| > N//4 that the reference applies IN PLACE to the state v (quirk Q4; in Burger_fd v is refreshed from u at
+    // the end of the step, so the filter has no lasting effect there).  X = unscaled fft(U^2), U = N u.
+    __device__ __forceinline__ static void dsm_sgs(const R& f, const Cx<T> (&X)[P], T XN, Cx<T> (&v)[P], Cx<T>& vN, const T (&kw)[P],
+                                                   T kwN, const Cx<T> (&ws1)[P], const Cx<T> (&dudx)[P], const Cx<T> (&d2)[P],
+                                                   T scale_nl, T invN, T inv_dx, Cx<T> (&sgs)[P]) {
+        Cx<T> z[P];
+        // dynamic Smagorinsky, Burger.py:357-399 (Germano identity with a sharp spectral
+        // test filter |k| > N//4 applied IN PLACE to the state v, :369-370)
+        const T delta = T(2.0 * 3.14159265358979323846 / N), deltah = T(4.0 * 3.14159265358979323846 / N);
+        bool cut[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) cut[p] = fabs(kw[p]) > T(N / 4);
+        const bool cutN = fabs(kwN) > T(N / 4);
+        Cx<T> w[P], L1[P], uh[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p)      // filtered fft(u^2) = 2 X
+            w[p] = cut[p] ? cx<T>(0, 0) : cx<T>((T(2) * scale_nl) * X[p].re, (T(2) * scale_nl) * X[p].im);
+        f.inv(w, cutN ? T(0) : (T(2) * scale_nl) * XN, L1);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            L1[p] = cx<T>(L1[p].re * (T(0.5) * invN), L1[p].im * (T(0.5) * invN));
+            if (cut[p]) v[p] = cx<T>(0, 0);
+        }
+        if (cutN) vN = cx<T>(0, 0);
+        f.inv(v, vN.re, uh);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            uh[p] = cx<T>(uh[p].re * invN, uh[p].im * invN);
+            z[p] = cx<T>(fabs(dudx[p].re) * dudx[p].re, fabs(dudx[p].im) * dudx[p].im);
+        }
+        Cx<T> W2[P], M1[P];
+        T W2N;
+        f.fwd(z, W2, W2N, T(1), ws1);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            if (cut[p]) W2[p] = cx<T>(0, 0);
+        f.inv(W2, cutN ? T(0) : W2N, M1);
+        T uhl[P], uhr[P];
+        halo(f, uh, uhl, uhr);
+        Cx<T> malt[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const T m1a = delta * delta * invN * M1[p].re, m1b = delta * delta * invN * M1[p].im;
+            const T da = (uh[p].re - uhl[p]) * inv_dx, db = (uh[p].im - uh[p].re) * inv_dx;
+            const T M2a = deltah * deltah * fabs(da) * da, M2b = deltah * deltah * fabs(db) * db;
+            malt[p] = cx<T>(T(4) / (deltah * deltah) * M2a - T(1) / (delta * delta) * m1a,
+                            T(4) / (deltah * deltah) * M2b - T(1) / (delta * delta) * m1b);
+        }
+        T ml[P], mr[P];
+        halo(f, malt, ml, mr);
+        T num = T(0), den = T(0);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const T Lga = L1[p].re - T(0.5) * uh[p].re * uh[p].re;
+            const T Lgb = L1[p].im - T(0.5) * uh[p].im * uh[p].im;
+            const T Mga = (malt[p].re - ml[p]) * inv_dx, Mgb = (malt[p].im - malt[p].re) * inv_dx;
+            num += -Lga * Mga - Lgb * Mgb;
+            den += Mga * Mga + Mgb * Mgb;
+        }
+        num = team_sum(f, num);
+        den = team_sum(f, den);
+        const T c = num / den;          // mean/mean: the 1/N cancels (Burger.py:397)
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            sgs[p] = cx<T>(c * fabs(dudx[p].re) * d2[p].re, c * fabs(dudx[p].im) * d2[p].im);
+    }
 
     __device__ static void run(const SpectralParams<T>& prm, T* smem) {
         const int lane = threadIdx.x & 31;
@@ -215,7 +283,7 @@ struct BurgersWarp {
         // ---- U = N * Re ifft(v) ---------------------------------------------------------------
         Cx<T> U[P], Uprev[P];
         // Burger_fd (generic kernel only): u is the primary variable and lives in the uprev slot; v = fft(u) is derived
-        const bool fd = SF < 0 && (flags & F_FD);
+        constexpr bool fd = SF == -2;          // Burger_fd has its own instantiation: the generic kernel (SF = -1) carries none of it
         if (fd) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -228,10 +296,12 @@ struct BurgersWarp {
 #pragma unroll
         for (int p = 0; p < P; ++p) Uprev[p] = U[p];
         const bool v1 = !LEAN && prm.version == 1;             // state version 1 needs u of the previous step (dudt)
+        // Burger_fd keeps u itself in the uprev slot; its previous row lives in the (otherwise unused) Fn_old slot
+        const Cx<T>* const uprev_row = fd ? reinterpret_cast<const Cx<T>*>(prm.fn + ec * NH) : reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N);
         if ((flags & F_NO_ADVANCE) && v1 && iout > 0) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const Cx<T> t = ldcx(reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N) + p * TS + tl);
+                const Cx<T> t = ldcx(uprev_row + p * TS + tl);
                 Uprev[p] = cx<T>(t.re * T(N), t.im * T(N));
             }
         }
@@ -321,7 +391,20 @@ struct BurgersWarp {
                 for (int k = 0; k < 3; ++k) c3[k] = ldcx(fc_row + col * 3 + k);
                 col = (col + 1 == prm.stepper) ? 0 : col + 1;
             }
-            Cx<T> zz[P];
+            Cx<T> zz[P], sgs_d[P];
+            if (flags & F_DSM) {               // dynamic Smagorinsky (Burger_fd.py:358-411): same closure as the spectral solver
+                Cx<T> dudx_c[P], d2_c[P], X2[P];
+                T X2N;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const T ue = U[p].re * invN, uo = U[p].im * invN, ul = left[p] * invN, ur = right[p] * invN;
+                    dudx_c[p] = cx<T>((ue - ul) * inv_dx, (uo - ue) * inv_dx);
+                    d2_c[p] = cx<T>((uo - T(2) * ue + ul) * inv_dx2, (ur - T(2) * uo + ue) * inv_dx2);
+                    zz[p] = cx<T>(U[p].re * U[p].re, U[p].im * U[p].im);
+                }
+                f.fwd(zz, X2, X2N, T(1), ws1);
+                dsm_sgs(f, X2, X2N, v, vN, kw, kwN, ws1, dudx_c, d2_c, scale_nl, invN, inv_dx, sgs_d);
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 if (it == nsub - 1) Uprev[p] = U[p];
@@ -336,6 +419,7 @@ struct BurgersWarp {
                 for (int h = 0; h < 2; ++h) {
                     T forc = T(0);
                     if (flags & F_SSM) forc = (T(0.1) * delta) * (T(0.1) * delta) * fabs(dudx[h]) * d2[h];             // :343-355
+                    if (flags & F_DSM) forc = h == 0 ? sgs_d[p].re : sgs_d[p].im;
                     if (flags & F_FORCING) {           // f_j = (2/N) Re sum_k c_k exp(2 pi i k j / N)  (:406-417, replaces)
                         const int j = 2 * (p * TS + tl) + h;
                         forc = T(0);
@@ -411,65 +495,7 @@ struct BurgersWarp {
                     for (int p = 0; p < P; ++p)
                         sgs[p] = cx<T>(cd2 * fabs(dudx[p].re) * d2[p].re, cd2 * fabs(dudx[p].im) * d2[p].im);
                 } else {
-                    // dynamic Smagorinsky, Burger.py:357-399 (Germano identity with a sharp spectral
-                    // test filter |k| > N//4 applied IN PLACE to the state v, :369-370)
-                    const T delta = T(2.0 * 3.14159265358979323846 / N), deltah = T(4.0 * 3.14159265358979323846 / N);
-                    bool cut[P];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) cut[p] = fabs(kw[p]) > T(N / 4);
-                    const bool cutN = fabs(kwN) > T(N / 4);
-                    Cx<T> w[P], L1[P], uh[P];
-#pragma unroll
-                    for (int p = 0; p < P; ++p)      // filtered fft(u^2) = 2 X
-                        w[p] = cut[p] ? cx<T>(0, 0) : cx<T>((T(2) * scale_nl) * X[p].re, (T(2) * scale_nl) * X[p].im);
-                    f.inv(w, cutN ? T(0) : (T(2) * scale_nl) * XN, L1);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        L1[p] = cx<T>(L1[p].re * (T(0.5) * invN), L1[p].im * (T(0.5) * invN));
-                        if (cut[p]) v[p] = cx<T>(0, 0);
-                    }
-                    if (cutN) vN = cx<T>(0, 0);
-                    f.inv(v, vN.re, uh);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        uh[p] = cx<T>(uh[p].re * invN, uh[p].im * invN);
-                        z[p] = cx<T>(fabs(dudx[p].re) * dudx[p].re, fabs(dudx[p].im) * dudx[p].im);
-                    }
-                    Cx<T> W2[P], M1[P];
-                    T W2N;
-                    f.fwd(z, W2, W2N, T(1), ws1);
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        if (cut[p]) W2[p] = cx<T>(0, 0);
-                    f.inv(W2, cutN ? T(0) : W2N, M1);
-                    T uhl[P], uhr[P];
-                    halo(f, uh, uhl, uhr);
-                    Cx<T> malt[P];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const T m1a = delta * delta * invN * M1[p].re, m1b = delta * delta * invN * M1[p].im;
-                        const T da = (uh[p].re - uhl[p]) * inv_dx, db = (uh[p].im - uh[p].re) * inv_dx;
-                        const T M2a = deltah * deltah * fabs(da) * da, M2b = deltah * deltah * fabs(db) * db;
-                        malt[p] = cx<T>(T(4) / (deltah * deltah) * M2a - T(1) / (delta * delta) * m1a,
-                                        T(4) / (deltah * deltah) * M2b - T(1) / (delta * delta) * m1b);
-                    }
-                    T ml[P], mr[P];
-                    halo(f, malt, ml, mr);
-                    T num = T(0), den = T(0);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const T Lga = L1[p].re - T(0.5) * uh[p].re * uh[p].re;
-                        const T Lgb = L1[p].im - T(0.5) * uh[p].im * uh[p].im;
-                        const T Mga = (malt[p].re - ml[p]) * inv_dx, Mgb = (malt[p].im - malt[p].re) * inv_dx;
-                        num += -Lga * Mga - Lgb * Mgb;
-                        den += Mga * Mga + Mgb * Mgb;
-                    }
-                    num = team_sum(f, num);
-                    den = team_sum(f, den);
-                    const T c = num / den;          // mean/mean: the 1/N cancels (Burger.py:397)
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        sgs[p] = cx<T>(c * fabs(dudx[p].re) * d2[p].re, c * fabs(dudx[p].im) * d2[p].im);
+                    dsm_sgs(f, X, XN, v, vN, kw, kwN, ws1, dudx, d2, scale_nl, invN, inv_dx, sgs);
                 }
                 Cx<T> G[P];
                 T GN;
@@ -592,16 +618,18 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 stcx(prm.v + e * NH + kk[p], v[p]);
-                stcx(prm.fn + e * NH + kk[p], fn[p]);
+                if (!fd) stcx(prm.fn + e * NH + kk[p], fn[p]);
                 prm.acc[e * NH + kk[p]] = acc32[p];
-                if (fd)                    // Burger_fd: the field itself is the primary variable
+                if (fd) {                  // Burger_fd: the field itself is the primary variable
                     stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(U[p].re * invN, U[p].im * invN));
-                else if (v1)               // u before the last sub-step: only state version 1 (dudt) reads it
+                    if (v1) stcx(reinterpret_cast<Cx<T>*>(prm.fn + e * NH) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
+                } else if (v1) {           // u before the last sub-step: only state version 1 (dudt) reads it
                     stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + p * TS + tl, cx<T>(Uprev[p].re * invN, Uprev[p].im * invN));
+                }
             }
             if (f.dc) {
                 stcx(prm.v + e * NH + H, vN);
-                stcx(prm.fn + e * NH + H, cx<T>(T(0), fnN));
+                if (!fd) stcx(prm.fn + e * NH + H, cx<T>(T(0), fnN));
                 prm.acc[e * NH + H] = accN;
                 prm.iout[e] = iout;
                 prm.tnow[e] = tnow;

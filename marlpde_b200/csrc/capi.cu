@@ -61,6 +61,7 @@ struct mpde_env {
                               void* err, int64_t timeout_us) = 0;
     virtual int step_fused(const void* actions, int nsub, void* state_out, void* reward_out, int async, cudaStream_t st) = 0;
     virtual int peer_join(cudaStream_t st) = 0;
+    virtual int compute_sgs(int nURG, int64_t rows, void* sgs, void* alt, void* alt2, cudaStream_t st) = 0;
     virtual int get(int field, void* dst, cudaStream_t st) = 0;
     virtual int set(int field, const void* src, cudaStream_t st) = 0;
     int64_t state_size() const {
@@ -72,6 +73,7 @@ struct mpde_env {
             return (int64_t)A * (nf * seg + tail);
         }
         if (cfg.equation == MPDE_KS) return 2 * N;
+        if (cfg.equation == MPDE_LAPLACE) return 4 * (int64_t)(N - 1);
         return A == 1 ? N : (int64_t)A * (N / A + 2);
     }
 };
@@ -388,7 +390,9 @@ struct Env : mpde_env {
         if (actions) {
             if (cfg.M <= 0) return fail("step: actions given but M == 0 (call setup_basis / set M first)");
             if (spectral() && !basis_set) return fail("step: actions given but no basis was set");
-            if (cfg.equation == MPDE_DIFFUSION && cfg.M != 1 && cfg.M != cfg.N) return fail("step: Diffusion takes 1 or N actions");
+            if ((cfg.equation == MPDE_DIFFUSION || cfg.equation == MPDE_DIFFUSION_ERROR) && cfg.M != 1 && cfg.M != cfg.N)
+                return fail("step: Diffusion takes 1 or N actions");
+            if (cfg.equation == MPDE_LAPLACE && cfg.M != 3 * (cfg.N - 1)) return fail("step: Laplace takes 3 (N - 1) actions");
             if (cfg.equation == MPDE_ADVECTION && cfg.M != 2 && cfg.M != 2 * cfg.N) return fail("step: Advection takes 2 or 2N actions");
             flags |= F_ACTIONS;
             if (basis_dense) flags |= F_BASIS_DENSE;
@@ -472,7 +476,8 @@ struct Env : mpde_env {
         const int parity = peer_bound ? (int)(peer_steps & 1) : 0;
         const size_t B = (size_t)cfg.nenvs;
         const size_t na = actions ? B * (size_t)cfg.M : 0, ns = state_out ? B * (size_t)state_size() : 0;
-        const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? cfg.N : cfg.num_agents) : 0;
+        const size_t nr = reward_out ? B * (size_t)(cfg.reward_mode == MPDE_REWARD_DIRECT ? (cfg.equation == MPDE_LAPLACE ? cfg.N - 1 : cfg.N)
+                                                                                             : cfg.num_agents) : 0;
         if (na > stage_act_n) { if (dalloc(&stage_act, na)) return -1; stage_act_n = na; ++epoch; }
         if (ns + nr > stage_out_n) { if (dalloc(&stage_out, ns + nr + 2)) return -1; stage_out_n = ns + nr; ++epoch; }
         static const bool use_graph = [] { const char* s = std::getenv("MPDE_HOST_GRAPH"); return !(s && s[0] == '0'); }();
@@ -613,6 +618,21 @@ struct Env : mpde_env {
         return rc;
     }
 
+    int compute_sgs(int nURG, int64_t rows, void* sgs, void* alt, void* alt2, cudaStream_t st) override {
+        CU(cudaSetDevice(cfg.device));
+        if (!spectral()) return fail("compute_sgs: spectral solvers only");
+        if (!prm.uu_hist || prm.hist_rows < 2) return fail("compute_sgs: needs the uu history (mpde_set_history) with at least two rows");
+        if (rows < 2 || rows > prm.hist_rows) return fail("compute_sgs: rows must be in 2..hist_rows");
+        if (nURG < 2 || nURG > 64 || nURG > cfg.N) return fail("compute_sgs: nURG must be in 2..64");
+        if (!sgs) return fail("compute_sgs: null output");
+        if (rows != prm.hist_rows) return fail("compute_sgs: rows must equal the history length (the reference scans uu.shape[0] rows)");
+        const int rc = launch_sgs<T>(prm, prm.uu_hist, rows, nURG, cfg.equation == MPDE_KS ? 1 : 0, sgs, alt, alt2, st);
+        if (rc < 0) return fail("compute_sgs: N must be 256, 512, 1024 or 2048");
+        launches += rc;
+        CU(cudaGetLastError());
+        return 0;
+    }
+
     int get(int field, void* dst, cudaStream_t st) override {
         CU(cudaSetDevice(cfg.device));
         const int64_t B = cfg.nenvs;
@@ -704,6 +724,7 @@ int mpde_create(const mpde_config* cfg, mpde_env** out) {
     if (cfg->struct_size != (int32_t)sizeof(mpde_config)) return fail("create: mpde_config size mismatch (ABI)");
     if (cfg->nenvs <= 0) return fail("create: nenvs must be positive");
     if (cfg->N < 4) return fail("create: N must be >= 4");
+    if (cfg->equation < MPDE_BURGERS || cfg->equation > MPDE_LAPLACE) return fail("create: unknown equation");
     if ((cfg->equation == MPDE_BURGERS || cfg->equation == MPDE_KS) && cfg->N < 8) return fail("create: spectral solvers need N >= 8");
     const bool spectral = cfg->equation == MPDE_BURGERS || cfg->equation == MPDE_KS;
     if (spectral && !is_pow2(cfg->N)) return fail("create: spectral solvers need a power-of-two N");
@@ -714,8 +735,7 @@ int mpde_create(const mpde_config* cfg, mpde_env** out) {
     if (cfg->flags & MPDE_FD) {
         if (cfg->equation != MPDE_BURGERS) return fail("create: MPDE_FD is a Burgers option (Burger_fd)");
         if (cfg->N > 256) return fail("create: Burger_fd is available for N <= 256");
-        if (cfg->flags & MPDE_DSM) return fail("create: Burger_fd with the dynamic Smagorinsky closure is not supported");
-        if (cfg->version == 1 || cfg->version > 2) return fail("create: Burger_fd supports state versions 0 and 2");
+        if (cfg->version > 2) return fail("create: Burger_fd has state versions 0, 1 and 2 (Burger_fd.py:590-640)");
     }
     if (cfg->version < 0 || cfg->version > 4) return fail("create: version must be 0..4");
     if (!(cfg->L > 0) || !(cfg->dt > 0)) return fail("create: L and dt must be positive");
@@ -818,6 +838,9 @@ int mpde_step_fused(mpde_env* env, const void* actions, int32_t nsub, void* stat
     return env ? env->step_fused(actions, nsub, state_out, reward_out, async_gather, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }
 int mpde_peer_join(mpde_env* env, void* stream) { return env ? env->peer_join(static_cast<cudaStream_t>(stream)) : fail("null argument"); }
+int mpde_compute_sgs(mpde_env* env, int32_t nURG, int64_t rows, void* sgs_out, void* alt_out, void* alt2_out, void* stream) {
+    return env ? env->compute_sgs(nURG, rows, sgs_out, alt_out, alt2_out, static_cast<cudaStream_t>(stream)) : fail("null argument");
+}
 int mpde_get(mpde_env* env, int32_t field, void* dst, void* stream) {
     return env && dst ? env->get(field, dst, static_cast<cudaStream_t>(stream)) : fail("null argument");
 }

@@ -1,6 +1,8 @@
 // Launchers of the CTA-per-environment spectral kernels (N = 256..2048): Burgers / KS DNS.
 #include "dispatch.h"
 #include "spectral_cta.cuh"
+#include "dns_warp.cuh"
+#include <map>
 
 namespace mpde {
 
@@ -15,19 +17,42 @@ static int launch_cta(const SpectralParams<T>& p, cudaStream_t st) {
     if (p.flags & (F_SSM | F_DSM)) return -2;                          // closures: warp kernels only
     if (p.reward_mode == REWARD_MSE && p.reward_out) return -3;        // MSE reward: warp kernels only
     const size_t smem = SpectralCta<T, N, NT, EQ>::smem_bytes(p.M);
-    static size_t configured = 48 * 1024;       // dynamic shared memory above 48 KB is opt-in (227 KB max on sm_100)
+    // dynamic shared memory above 48 KB is opt-in (227 KB max on sm_100); the attribute is per DEVICE, so the bookkeeping is too
+    static std::map<int, size_t> configured;
     if (smem > 227 * 1024) return -5;
-    if (smem > configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = configured.emplace(dev, 48 * 1024).first->second;
+    if (smem > have) {
         if (cudaFuncSetAttribute(spectral_cta_kernel<T, N, NT, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return -4;
-        configured = smem;
+        have = smem;
     }
     spectral_cta_kernel<T, N, NT, EQ><<<(unsigned)p.B, NT, smem, st>>>(p);
     return 1;
 }
 
+// N = 1024 Burgers DNS (no actions / closures / state / reward): one warp per environment, state in registers (dns_warp.cuh)
+template <typename T>
+__global__ void __launch_bounds__(32) burgers_dns1024_kernel(const SpectralParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Dns1024<T>::run(prm, smem_raw);
+}
+template <typename T>
+static bool dns_warp_eligible(const SpectralParams<T>& p) {
+    static const bool on = [] { const char* s = std::getenv("MPDE_DNS_WARP"); return !(s && s[0] == '0'); }();
+    return on && p.N == 1024 && !(p.flags & (F_ACTIONS | F_SSM | F_DSM | F_FD | F_NO_ADVANCE)) && p.nsub > 0 && !p.state_out && !p.reward_out;
+}
+template <typename T>
+static int launch_dns1024(const SpectralParams<T>& p, cudaStream_t st) {
+    const size_t smem = Dns1024<T>::smem_bytes();
+    burgers_dns1024_kernel<T><<<(unsigned)p.B, 32, smem, st>>>(p);
+    return 1;
+}
+
 template <typename T, int EQ>
 static int launch_cta_n(const SpectralParams<T>& p, cudaStream_t st) {
+    if (EQ == 0 && dns_warp_eligible(p)) return launch_dns1024<T>(p, st);
     switch (p.N) {
         case 256: return launch_cta<T, 256, 32, EQ>(p, st);
         case 512: return launch_cta<T, 512, 64, EQ>(p, st);
@@ -45,7 +70,10 @@ static int launch_aux_cta(const SpectralParams<T>& p, int equation, int mode, co
                           cudaStream_t st) {
     constexpr int H = N / 2, NH = H + 1;
     const size_t smem = sizeof(Cx<T>) * (2 * H + 2 * NH) + 16;
-    static bool configured = false;
+    static std::map<int, bool> configured_dev;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev];
     if (!configured && smem > 48 * 1024) {
         cudaFuncSetAttribute(aux_cta_kernel<T, N, NT, AUX_RESET_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(aux_cta_kernel<T, N, NT, AUX_RESET_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

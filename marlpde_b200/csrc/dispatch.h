@@ -30,6 +30,8 @@ template <typename T>
 int launch_turbulence(const long long* seed, const double* offset, const double* x, const double* amp, const uint8_t* mask,
                       void* out, int64_t B, int N, double L, cudaStream_t st);
 template <typename T> int launch_ks_cta(const SpectralParams<T>& p, cudaStream_t st);
+template <typename T>
+int launch_sgs(const SpectralParams<T>& p, const void* uu, int64_t rows, int nURG, int ks, void* sgs, void* alt, void* alt2, cudaStream_t st);
 template <typename T> int launch_fd(const SpectralParams<T>& p, int equation, bool implicit, cudaStream_t st);
 template <typename T> int launch_fd_reset(const SpectralParams<T>& p, const void* src, const uint8_t* mask, cudaStream_t st);
 template <typename T>

@@ -1,5 +1,6 @@
-// Finite-difference environments: Diffusion (Diffusion.py:137-216, 238-298) and Advection
-// (Advection.py:138-213, 235-286).  The reference builds a dense N x N matrix per step and
+// Finite-difference environments: Diffusion (Diffusion.py:137-216, 238-298), Advection
+// (Advection.py:138-213, 235-286), DiffusionError (DiffusionError.py:137-216: the action perturbs the Laplacian
+// stencil) and Laplace (Laplace.py:116-166: relaxation with three free stencil entries per agent, one Dirichlet point).  The reference builds a dense N x N matrix per step and
 // evaluates M @ u; M is a periodic tridiagonal stencil whose entries are the agents' actions,
 // so the kernel applies the 3-point stencil directly.  One warp per environment, the row u and
 // the three coefficient rows live in shared memory, `nsub` steps are fused per launch.
@@ -7,7 +8,7 @@
 
 namespace mpde {
 
-constexpr int EQ_DIFFUSION = 2, EQ_ADVECTION = 3;
+constexpr int EQ_DIFFUSION = 2, EQ_ADVECTION = 3, EQ_DIFFUSION_ERROR = 4, EQ_LAPLACE = 5;
 
 template <typename T>
 __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm, int equation, int implicit) {
@@ -34,6 +35,19 @@ __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm
             // one global weight a -> (-a/2, a, -a/2) (Diffusion.py:172-178); per point a_k (:186-200)
             const T a = has_act ? act[prm.M == 1 ? 0 : n] : T(-2);
             l = -a / T(2); d = a; u = -a / T(2);
+        } else if (equation == EQ_DIFFUSION_ERROR) {
+            // the action is the ERROR of the stencil: (1 - a/2, -2 + a, 1 - a/2) (DiffusionError.py:166-190); with ONE agent
+            // the two wrap-around entries are M[0,-1] = 1 - ac[0] and M[-1,0] = 1 + ac[2], as the reference writes them (:171-172)
+            const T a = has_act ? act[prm.M == 1 ? 0 : n] : T(0);
+            l = T(1) - a / T(2); d = T(-2) + a; u = T(1) - a / T(2);
+            if (has_act && prm.M == 1) {
+                if (n == 0) l = T(1) - (T(1) - a / T(2));
+                if (n == N - 1) u = T(1) + (T(1) - a / T(2));
+            }
+        } else if (equation == EQ_LAPLACE) {
+            // row n = i + 1 of agent i: entries on columns i, i + 1, (i + 2) % N; row 0 stays zero (Laplace.py:121-129)
+            if (has_act && n >= 1) { l = act[3 * (n - 1)]; d = act[3 * (n - 1) + 1]; u = act[3 * (n - 1) + 2]; }
+            else { l = T(0); d = T(0); u = T(0); }
         } else {
             if (!has_act) {           // Lax (Advection.py:142-148), alpha = nu dt / dx as set at construction
                 const T al = prm.etd[e];
@@ -55,7 +69,7 @@ __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm
     T* cur = ua;
     T* nxt = ub;
     for (int it = 0; it < nsub; ++it) {
-        if (equation == EQ_DIFFUSION && !has_act && implicit) {
+        if ((equation == EQ_DIFFUSION || equation == EQ_DIFFUSION_ERROR) && !has_act && implicit) {
             // implicit Euler: (I - c Lap) u' = u, periodic tridiagonal (Diffusion.py:142-149), solved by the
             // Thomas algorithm with a Sherman-Morrison correction for the two corner entries
             if (lane == 0) {
@@ -90,7 +104,7 @@ __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm
             for (int n = lane; n < N; n += 32) {
                 const T um = cur[n == 0 ? N - 1 : n - 1], u0 = cur[n], upv = cur[n == N - 1 ? 0 : n + 1];
                 T r;
-                if (equation == EQ_DIFFUSION && !has_act) {
+                if ((equation == EQ_DIFFUSION || equation == EQ_DIFFUSION_ERROR) && !has_act) {
                     // explicit Euler, standard Laplacian (Diffusion.py:156-160)
                     const T d2 = (T(-2) * u0 + um + upv) / (dx * dx);
                     r = u0 + dt * nu * d2;
@@ -98,7 +112,9 @@ __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm
                     const T a = lo[n] * um, b = di[n] * u0, c = up[n] * upv;
                     // a dense row-times-vector sums in column order: rows 0 and N-1 wrap
                     const T mv = n == 0 ? (b + c) + a : (n == N - 1 ? (c + a) + b : (a + b) + c);
-                    r = equation == EQ_DIFFUSION ? u0 + dt * nu * mv / (dx * dx) : mv;       // Diffusion.py:206 / Advection.py:200
+                    if (equation == EQ_ADVECTION) r = mv;                                           // Advection.py:200
+                    else if (equation == EQ_LAPLACE) r = n == 0 ? T(1) : u0 + dt * mv;            // Laplace.py:131-136 (u[0] = 1)
+                    else r = u0 + dt * nu * mv / (dx * dx);                                       // Diffusion.py:206, DiffusionError.py:195
                 }
                 nxt[n] = r;
                 bad |= !(fabs((double)r) <= 1.79e308);
@@ -122,6 +138,28 @@ __global__ void __launch_bounds__(32) fd_step_kernel(const SpectralParams<T> prm
     }
     const T inf = T(1) / T(0);
     const int A = prm.A;
+    if (equation == EQ_LAPLACE) {
+        // force row: prm.truth [ntruth][1][N]; state [u_{i-1}, u_i, u_{i+1}, force_i] for i < N - 1 (Laplace.py:162-166);
+        // direct reward -(u_xx - force)^2 on points 1..N-1 (:153-160)
+        const T* force = prm.truth ? prm.truth + (prm.truth_map ? prm.truth_map[e] : 0) * prm.truth_rows * N : nullptr;
+        const int nA = N - 1;
+        if (prm.state_out && force) {
+            for (int o = lane; o < 4 * nA; o += 32) {
+                const int i = o >> 2, c = o & 3;
+                const T val = c == 3 ? force[i] : cur[(i - 1 + c + N) % N];
+                prm.state_out[e * 4 * nA + o] = live ? val : inf;
+            }
+        }
+        if (prm.reward_out && prm.reward_mode == REWARD_DIRECT && force) {
+            for (int n = 1 + lane; n < N; n += 32) {
+                const T um = cur[n - 1], u0 = cur[n], upv = cur[n == N - 1 ? 0 : n + 1];
+                const T d2 = (T(-2) * u0 + um + upv) / (dx * dx);
+                const T df = d2 - force[n];
+                prm.reward_out[e * nA + (n - 1)] = live ? -(df * df) : -inf;
+            }
+        }
+        return;
+    }
     if (prm.state_out) {      // getState: u, or per-agent windows with a one-point halo (Diffusion.py:284-298)
         const int seg = A == 1 ? N : N / A + 2;
         const int S = A * seg;

@@ -12,7 +12,6 @@ from .common import laplacian_fd, upwind_fd
 class BurgerFdOracle(BurgerOracle):
     def __init__(self, *a, ssmforce=False, **kw):
         super().__init__(*a, **kw)
-        assert not self.dsm, "dynamic Smagorinsky of Burger_fd is not restated"
         self.ssmforce = ssmforce
 
     def step(self, actions=None):
@@ -22,6 +21,8 @@ class BurgerFdOracle(BurgerOracle):
         forcing = np.zeros((B, N))
         if self.ssm:                                            # :343-355
             forcing = self._static_smagorinsky()
+        if self.dsm:                                            # :358-411: the same closure as Burger.step (filters self.v in place;
+            forcing = self._dynamic_smagorinsky()               # v is refreshed from u below, so nothing of it survives the step)
         if self.forcing:                                        # :406-417 (replaces the closure)
             forcing = self._stochastic()
         if actions is not None:                                 # :431-458

@@ -20,13 +20,17 @@ CASES = {
     "fd_ssmforce": dict(dforce=True, ssmforce=True, act=(0.0, 0.3)),
     "fd_sinus64": dict(N=64, case="sinus", dforce=False, M=16, act=(-0.01, 0.03)),
     "fd_forced_s4": dict(forcing=True, stepper=4, dforce=True, act=(-0.5, 0.5)),
+    "fd_dsm": dict(dsm=True, M=0),
+    "fd_dsm_eddy": dict(dsm=True, dforce=False, act=(-0.01, 0.03)),
+    "fd_v1": dict(dforce=False, act=(-0.01, 0.03), version=1),
+    "fd_v2": dict(dforce=True, act=(-1.0, 1.0), version=2),
 }
 
 
-def run(N=32, nsteps=60, hold=10, case="turbulence", forcing=False, dforce=True, ssmforce=False, ssm=False, stepper=1, M=32,
-        basis="hat", act=None, seed=42, version=0):
+def run(N=32, nsteps=60, hold=10, case="turbulence", forcing=False, dforce=True, ssmforce=False, ssm=False, dsm=False, stepper=1,
+        M=32, basis="hat", act=None, seed=42, version=0):
     b = RF.Burger_fd(L=2 * np.pi, N=N, dt=1e-3, nu=0.02, nsteps=nsteps, case=case, forcing=forcing, dforce=dforce,
-                     ssmforce=ssmforce, ssm=ssm, seed=seed, s=stepper, version=version)
+                     ssmforce=ssmforce, ssm=ssm, dsm=dsm, seed=seed, s=stepper, version=version)
     if M:
         b.setup_basis(M, basis)
     rng = np.random.default_rng(11)

@@ -95,3 +95,47 @@ def test_known_answers_and_batching():
         a1.step([0.5 + 0.5 * al, 0.5 - 0.5 * al])
     assert rel(a0.u, a1.u.cpu().numpy()) < 1e-13
     assert rel(a0.u, a0.getAnalyticalSolution(a0.t)) < 2e-2
+
+
+@pytest.mark.parametrize("tag,agents", [("de_noact", 0), ("de_one", 1), ("de_marl", 32), ("de_box", 32)])
+def test_diffusion_error(golden, tag, agents):
+    """DiffusionError.step / getMseReward / getState (DiffusionError.py:160-298) against goldens recorded from the reference
+    class; batch of 3 identical environments must agree bitwise."""
+    from marlpde_b200 import DiffusionError
+    g = golden("fd_extra.npz")
+    U, A = g[f"{tag}/u"], g[f"{tag}/actions"]
+    case = "box" if tag == "de_box" else "sinus"
+    d = DiffusionError(L=2 * np.pi, N=U.shape[1], dt=1e-3, nu=0.05, nsteps=len(U) - 1, case=case, nenvs=3)
+    assert np.array_equal(d.u.cpu().numpy()[0], U[0])
+    for i in range(len(U) - 1):
+        if agents == 0:
+            d.step()
+        else:
+            d.step(np.tile(A[i].reshape(1, -1), (3, 1)), agents)
+        u = d.u.cpu().numpy()
+        assert np.array_equal(u[0], u[1]) and np.array_equal(u[0], u[2])
+        assert np.max(np.abs(u[0] - U[i + 1])) <= 1e-12 * max(1.0, np.max(np.abs(U[i + 1]))), (tag, i)
+    if case == "sinus":
+        rw = d.getMseReward(max(agents, 1)).cpu().numpy()[0]
+        np.testing.assert_allclose(rw, g[f"{tag}/reward"], rtol=1e-8, atol=1e-18)
+    np.testing.assert_allclose(d.getState(1).cpu().numpy()[0], g[f"{tag}/state"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag,sforce,ic", [("lp_sin", "sin", "one"), ("lp_gauss", "gaussian", "sin")])
+def test_laplace(golden, tag, sforce, ic):
+    """Laplace.step / getDirectReward / getState (Laplace.py:116-166) against goldens recorded from the reference class."""
+    from marlpde_b200 import Laplace
+    g = golden("fd_extra.npz")
+    U, A, R = g[f"{tag}/u"], g[f"{tag}/actions"], g[f"{tag}/reward"]
+    lp = Laplace(L=2 * np.pi, N=U.shape[1] - 1, dt=0.01, ic=ic, sforce=sforce, episodeLength=len(U) - 1, nenvs=2)
+    nA = lp.N - 1
+    assert np.max(np.abs(lp.u.cpu().numpy()[0] - U[0])) <= 1e-15 and np.max(np.abs(lp.force[0] - g[f"{tag}/force"])) <= 1e-15
+    for i in range(len(U) - 1):
+        _, rw = lp.step_n(np.tile(A[i].reshape(1, -1), (2, 1)), nA, 1, want_reward=True)
+        u = lp.u.cpu().numpy()
+        assert np.array_equal(u[0], u[1])
+        assert np.max(np.abs(u[0] - U[i + 1])) <= 1e-12 * max(1.0, np.max(np.abs(U[i + 1]))), (tag, i)
+        np.testing.assert_allclose(rw.cpu().numpy()[0], R[i], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(np.asarray(lp.getDirectReward(nA).cpu().numpy()[0]), R[i], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(lp.getState(nA).cpu().numpy()[0], g[f"{tag}/state"], rtol=1e-12, atol=1e-13)
+    assert np.array_equal(lp.uu.cpu().numpy()[0, -1], u[0])

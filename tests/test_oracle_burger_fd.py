@@ -13,6 +13,10 @@ FD_CASES = {
     "fd_ssmforce": dict(dforce=True, ssmforce=True),
     "fd_sinus64": dict(N=64, dforce=False, M=16),
     "fd_forced_s4": dict(forcing=True, stepper=4, dforce=True),
+    "fd_dsm": dict(dsm=True, M=0),
+    "fd_dsm_eddy": dict(dsm=True, dforce=False),
+    "fd_v1": dict(dforce=False, version=1),
+    "fd_v2": dict(dforce=True, version=2),
 }
 
 
