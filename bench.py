@@ -355,7 +355,7 @@ def gpu_arm(args):
         from marlpde_b200.dist import PeerGather
         for env in envs:
             pg = PeerGather(B * (S + RW), torch.float64, device, copies=2)
-            pg.fuse(env, B, S, RW, gather_state=not args.rewards_only)
+            pg.fuse(env, B, S, RW, gather_state=not args.rewards_only, learner=0 if args.gather == "learner" else None)
             gathers.append(pg)
 
     def one_step(i):
@@ -398,8 +398,8 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         return g_, n_k
 
-    chains = max(1, min(args.chains, pool))
-    if pool % chains:
+    chains = max(1, min(args.chains, pool, K))
+    if K > pool and pool % chains:
         chains = 1                          # a batch must stay on one chain (its launches are ordered by its stream)
     # every batch once outside any graph (module load, lazy set-up, first-use allocations)
     for i in range(pool):
@@ -433,14 +433,14 @@ def gpu_arm(args):
         return launched
 
     sampler = ClockSampler(local) if rank == 0 else None      # covers warm-up + timed + e2e regions
-    # warm-up: (a) >= 60 ms of the same graph so the SM clock has ramped before anything is timed, (b) a fresh episode,
+    # warm-up: (a) ~3000 steps of the same graph so the SM clock has ramped before anything is timed, (b) a fresh episode,
     # (c) the W steps the driver asks for (rounded up to whole replays of the graph)
-    t_ramp = time.perf_counter()
+    # (the number of replays is a function of K only: with a gather every rank must replay the same number of steps)
     ramp_steps = 0
-    while time.perf_counter() - t_ramp < 0.06 and ramp_steps < 3000:
+    for _ in range(max(2, 3000 // seg)):
         graph.replay()
         ramp_steps += seg
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     new_episode()
     warm_steps = 0
     while warm_steps < max(W, 3):
@@ -620,7 +620,12 @@ def gpu_arm(args):
         if world > 1:
             line["gather_parity"] = gather_parity
             line["transport"] = (("NVSwitch multicast (multimem.st), %s memory" if gathers[0].multicast else "unicast peer stores, %s memory")
-                                 % gathers[0].backend) + (", rewards only" if args.rewards_only else "")
+                                 % gathers[0].backend) + (", rewards only" if args.rewards_only else "") + \
+                                (", gathered to rank 0 only" if args.gather == "learner" else ", gathered to every rank")
+            nbytes = B * (RW + (0 if args.rewards_only else S)) * 8
+            line["gather_bytes_per_step"] = {"per_rank_slab": nbytes, "ingress_learner": nbytes * (world - 1 if args.gather == "learner" else world),
+                                             "ingress_other_ranks": 0 if args.gather == "learner" else nbytes * world,
+                                             "ingress_gbs_at_this_rate": nbytes * (world - 1 if args.gather == "learner" else world) / (ms * 1e-3 / K) / 1e9}
         if world == 1 and not args.quick:
             del pipe
             envs.clear()
@@ -758,6 +763,8 @@ def main():
     ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")
     ap.add_argument("--chains", type=int, default=4, help="independent batches in flight inside the replayed graph")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per environment (0 = library default)")
+    ap.add_argument("--gather", default="all", choices=["all", "learner"],
+                    help="multi-GPU: rows gathered to every rank (all-gather) or to rank 0 only (SURVEY 8e: gather semantics suffice)")
     ap.add_argument("--rewards-only", action="store_true", help="multi-GPU: gather only the rewards (configs[4] wording)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")
     args = ap.parse_args()

@@ -184,7 +184,7 @@ class Burger(SpectralEnv):
                 m, mp = self._mask_ptr(mask)
                 L_check(self._lib.mpde_reset_turbulence(self._h, self._ptr(sd), self._ptr(off), self._ptr(xd), self._ptr(ad), mp,
                                                         self._stream()))
-                self._after_reset()
+                self._after_reset(mask)
                 return
         if v0 is None:
             if u0 is None:
@@ -201,12 +201,7 @@ class Burger(SpectralEnv):
             v0d = self._batch(v0, self.cdtype, (N,))
             m, mp = self._mask_ptr(mask)
             L_check(self._lib.mpde_reset_v(self._h, self._ptr(torch.view_as_real(v0d)), mp, self._stream()))
-        self.t = 0.
-        self.stepnum = 0
-        self.ioutnum = 0
-        self._state_at = self._reward_at = -1
-        self.u0 = self.u
-        self.v0 = self.v
+        self._after_reset(mask)
 
     def _case_field(self, case):
         B, N = self.nenvs, self.N
@@ -425,6 +420,7 @@ class Burger(SpectralEnv):
 
     # ------------------------------------------------------------------ checkpoint
     def state_dict(self):
+        self._need_in_step("state_dict")
         B, N = self.nenvs, self.N
         return dict(v=self._get(LB.FIELD_V, (B, N), self.cdtype), Fn_old=self._get(LB.FIELD_FN_OLD, (B, N), self.cdtype),
                     u_prev=self._get(LB.FIELD_U_PREV, (B, N), self.dtype),

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmarlpde_b200.so")
+LIB_PATH = os.environ.get("MPDE_LIB_PATH") or os.path.join(_HERE, "libmarlpde_b200.so")     # override: tuning experiments only
 
 # enums (include/marlpde_b200.h)
 BURGERS, KS, DIFFUSION, ADVECTION, DIFFUSION_ERROR, LAPLACE = 0, 1, 2, 3, 4, 5

@@ -41,9 +41,23 @@ class SpectralEnv(BatchedEnv):
         m, mp = self._mask_ptr(mask)
         L_check(self._lib.mpde_reset_handoff(self._h, self._ptr(torch.view_as_real(v)), v.shape[0], v.shape[1], self._ptr(k),
                                              self._ptr(mp_t), self._ptr(off_t), mp, self._stream()))
-        self._after_reset()
+        self._after_reset(mask)
 
-    def _after_reset(self):
+    def _after_reset(self, mask=None):
+        """Host-side bookkeeping after an IC.  The device keeps ``ioutnum`` / ``t`` PER ENVIRONMENT (the kernels use those
+        for the forcing column and the reward row); the host scalars ``t``, ``ioutnum``, ``stepnum`` describe the whole
+        batch and are only meaningful while every environment is at the same step.  A MASKED reset of a running batch
+        breaks that: the scalars are left alone, ``_out_of_step`` is set, and everything that slices by the host scalar
+        (``compute_Ek``, ``uu`` / ``vv`` history views, ``state_dict``) raises until a full reset; per-environment
+        counters stay available through ``ioutnum_all`` / ``status``."""
+        partial = mask is not None and not bool(np.all(np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask) != 0))
+        if partial and getattr(self, "ioutnum", 0) != 0:
+            self._out_of_step = True
+            self._state_at = self._reward_at = -1
+            if hasattr(self, "_uu_valid_at"):
+                self._uu_valid_at = -1
+            return
+        self._out_of_step = False
         self.t = 0.
         self.stepnum = 0
         self.ioutnum = 0
@@ -96,7 +110,13 @@ class SpectralEnv(BatchedEnv):
         if burgers:
             self.sgsHistoryAlt, self.sgsHistoryAlt2 = self._squeeze(alt), self._squeeze(alt2)
 
+    def _need_in_step(self, what):
+        if getattr(self, "_out_of_step", False):
+            raise RuntimeError(f"{what}: a masked reset left the environments of this batch at different steps; the host-side "
+                               "scalars (t, ioutnum) no longer describe them -- use ioutnum_all / status, or reset the whole batch")
+
     def _need_history(self):
+        self._need_in_step("history / spectrum views")
         if not self.history:
             raise RuntimeError("history recording is off for this batch (pass history=True)")
 

@@ -151,6 +151,8 @@ class PeerGather:
         self._item = item
         self._steps_dev = torch.zeros(4, dtype=torch.int64, device=self.device)    # [0] published, [1] awaited
         self._fused = None
+        self.learner = None
+        self._wait_flags, self._wait_n, self._n_slots = self._my_flags, self.ws, self.ws
         self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         # error flag in mapped pinned host memory: the wait kernels write it, the host polls it without synchronising
         ep = C.c_void_p()
@@ -184,24 +186,41 @@ class PeerGather:
         self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err_ptr, self.timeout_us,
                                              self._stream()))
 
-    def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True):
+    def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True, learner=None):
         """Let ``env``'s step kernel write its [n_local,S] state and [n_local,A] reward straight into this rank's slab
-        of every rank's buffer and publish the step itself (no put kernel, no NCCL)."""
+        of every rank's buffer and publish the step itself (no put kernel, no NCCL).
+
+        ``learner=r``: GATHER instead of all-gather -- every rank stores its rows locally and into rank r's buffer only
+        (plain peer stores over NVLink); rank r waits for all ranks, the others only publish.  At 8 GPUs an all-gather
+        makes every rank ingest 8 slabs per step, a gather only the learner ("gather-style semantics suffice")."""
         C = self._C
         assert n_local * (S + A) == self.chunk_elems
         slab = self.rank * self.chunk_bytes
         mine = self._all[0, self.rank]
         env.bind_output(mine[:n_local * S].view(n_local, S), mine[n_local * S:].view(n_local, A))
-        others = [r for r in range(self.ws) if r != self.rank]
+        self.learner = learner
+        if learner is None:
+            others = [r for r in range(self.ws) if r != self.rank]
+        else:
+            others = [learner] if self.rank != learner else []
         arr_o = C.c_void_p * max(1, len(others))
         st = arr_o(*[self._peer_bases[r] + slab for r in others])
         rw = arr_o(*[self._peer_bases[r] + slab + n_local * S * self._item for r in others])
-        arr_f = C.c_void_p * self.ws
-        self._flag_slots = arr_f(*[self._peer_bases[r] + self.copies * self._copy_bytes + 8 * self.rank for r in range(self.ws)])
+        flag_base = self.copies * self._copy_bytes
+        # where this rank publishes its step counter: slot [rank] of every consumer's flag array (always its own too)
+        consumers = list(range(self.ws)) if learner is None else sorted({learner, self.rank})
+        arr_f = C.c_void_p * len(consumers)
+        self._flag_slots = arr_f(*[self._peer_bases[r] + flag_base + 8 * self.rank for r in consumers])
+        self._n_slots = len(consumers)
+        # what this rank waits for: every rank's slot (all-gather, or the learner of a gather) or only its own
+        if learner is None or self.rank == learner:
+            self._wait_flags, self._wait_n = self._my_flags, self.ws
+        else:
+            self._wait_flags, self._wait_n = self._my_flags + 8 * self.rank, 1
         stride = self._copy_bytes // self._item if self.copies == 2 else 0
         mc_state = mc_reward = None
         import os
-        if self.multicast_base and use_multicast and os.environ.get("MPDE_MULTICAST", "1") != "0":
+        if learner is None and self.multicast_base and use_multicast and os.environ.get("MPDE_MULTICAST", "1") != "0":
             # one multimem.st per row reaches every rank (this one included): no per-peer stores at all
             mc_reward = self.multicast_base + slab + n_local * S * self._item
             # gather_state=False: only the rewards travel (BASELINE configs[4]: "allgather of rewards"); the state rows
@@ -219,8 +238,8 @@ class PeerGather:
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         # publish / wait side of the fused step (mpde_step_fused: kernel -> publish -> wait as one host call)
-        rc = self._lib.mpde_set_peer_sync(env._h, self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._my_flags, self.ws,
-                                          self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us)
+        rc = self._lib.mpde_set_peer_sync(env._h, self._flag_slots, self._n_slots, self._steps_dev.data_ptr(), self._wait_flags,
+                                          self._wait_n, self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us)
         if rc != 0:
             raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         env._peer_host_ok = True
@@ -230,17 +249,17 @@ class PeerGather:
 
     def signal_next(self):
         """Enqueue (behind the step kernel in stream order) the publication of one more step to every rank."""
-        self._check(self._lib.mpde_peer_signal_next(self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._stream()))
+        self._check(self._lib.mpde_peer_signal_next(self._flag_slots, self._n_slots, self._steps_dev.data_ptr(), self._stream()))
 
     def exchange_next(self):
         """signal_next() + wait_next() as one kernel launch."""
-        self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self.ws, self._steps_dev.data_ptr(), self._my_flags, self.ws,
-                                                      self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us,
+        self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self._n_slots, self._steps_dev.data_ptr(), self._wait_flags,
+                                                      self._wait_n, self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us,
                                                       self._stream()))
 
     def wait_next(self):
         """Current stream waits until every rank has published one more step than the last wait_next() saw."""
-        self._check(self._lib.mpde_peer_wait_next(self._my_flags, self.ws, self._steps_dev[1:].data_ptr(), self._err_ptr,
+        self._check(self._lib.mpde_peer_wait_next(self._wait_flags, self._wait_n, self._steps_dev[1:].data_ptr(), self._err_ptr,
                                                   self.timeout_us, self._stream()))
 
     def current(self):
@@ -290,9 +309,12 @@ class ShardedBatch:
     single all-gather delivers to every rank (the learner reads ``states`` / ``rewards`` views).
     """
 
-    def __init__(self, n_global, factory, transport="nccl"):
+    def __init__(self, n_global, factory, transport="nccl", gather_to=None):
+        """``gather_to=r`` (transport "fused" only): rows are gathered to rank r alone (the learner); the other ranks see
+        their own rows in ``views()``."""
         self.rank, self.world_size = world()
         self.transport = transport
+        self.gather_to = gather_to
         self.n_global = int(n_global)
         self.lo, self.hi = shard_range(self.n_global, self.rank, self.world_size)
         self.ids = np.arange(self.lo, self.hi)
@@ -308,7 +330,7 @@ class ShardedBatch:
             if transport == "fused":
                 # the step kernel writes straight into every rank's (double-buffered) gather buffer
                 self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device, copies=2)
-                self._peer.fuse(self.env, nl, S, A)
+                self._peer.fuse(self.env, nl, S, A, learner=gather_to)
                 self._gflat = self._peer.gathered
             elif transport == "p2p":
                 self._peer = PeerGather(nl * (S + A), buf.dtype, buf.device, copies=2)

@@ -86,3 +86,40 @@ def environment(s, N, gridSize, numActions, dt, nu, episodeLength, dforce, seed,
     else:
         s["Termination"] = "Terminal"
     return sgs
+
+
+class KSEnvBatch:
+    """B copies of the episode above (ks_environment.py:36-120) stepped in lock-step on one GPU.
+
+    reset() -> states [B, 2 gridSize]; step(actions [B, M]) -> (states, rewards [B, 1], truncated [B] bool).
+    Environment e restarts from ``dns_default[e % len(dns_default)]`` (LES initial condition by spectral truncation of
+    that DNS's first history row, :52-54, as ONE hand-off launch for the whole batch) and is scored against that DNS's
+    time-averaged spectrum (:98-100)."""
+
+    def __init__(self, B, N, gridSize, numActions, dt, nu, episodeLength, dforce, seed, dns_default):
+        dns_list = list(dns_default) if isinstance(dns_default, (list, tuple)) else [dns_default]
+        self.B, self.gridSize, self.dns = int(B), gridSize, dns_list
+        d0 = dns_list[0]
+        self.nInt = int(tSim / dt / episodeLength)
+        self.episodeLength = episodeLength
+        self.dmap = np.arange(self.B) % len(dns_list)
+        self.sgs = KS(L=L, N=gridSize, dt=dt, nu=nu, tend=tSim, dforce=dforce, noise=0., nenvs=self.B, device=d0.device,
+                      history=False, u0=np.zeros(gridSize))
+        self.sgs.setup_basis(numActions, basis)
+        # first history row of every DNS (complex64, as the reference reads dns.vv[0]) on the device once
+        self._dns_v0 = torch.stack([torch.as_tensor(d.vv[0]).to(device=d0.device, dtype=torch.complex128).reshape(-1)
+                                    for d in dns_list])
+        self._dns_k = np.asarray(d0.k, dtype=np.float64)
+        ref = torch.cat([d._ektt[:, :, :gridSize // 2] for d in dns_list], dim=0)
+        self.sgs.set_spectrum_reference(ref, env_map=self.dmap if len(dns_list) > 1 else None)
+        self.step_count = 0
+
+    def reset(self):
+        self.sgs.IC_handoff(self._dns_v0, self._dns_k, src_map=self.dmap if len(self.dns) > 1 else None)
+        self.step_count = 0
+        return self.sgs.getState(as_tensor=True)
+
+    def step(self, actions):
+        st, rw = self.sgs.step_n(actions, self.nInt)
+        self.step_count += 1
+        return st, rw, self.sgs.status != 0

@@ -134,3 +134,27 @@ def test_ks_dns_setup_runs_and_has_the_reference_spectrum(golden):
     assert dns.ioutnum == 2000 and int(dns.status) == 0
     ek = dns.Ek_ktt.cpu().numpy()[-1, 1:9]
     np.testing.assert_allclose(ek, g["dns_Ek_ktt"][-1, 1:9], rtol=0.35)
+
+
+def test_ks_batched_episode_equals_single_sample_episodes(golden):
+    """KSEnvBatch (B environments in lock-step, device-side hand-off) == B runs of ks_environment.environment, bitwise."""
+    import marlpde_b200.ks_environment as ke
+    g = golden("ks_env.npz")
+    dns = ke.setup_dns_default(256, 0.25, 1.0, 42, u0=g["transient_u0"])
+    gsz, M, epl, B = 32, 16, 50, 3
+    rng = np.random.default_rng(4)
+    acts = rng.normal(0.0, 0.05, (B, epl, M))
+    env = ke.KSEnvBatch(B, 256, gsz, M, 0.25, 1.0, epl, True, 42, dns)
+    st0 = env.reset().cpu().numpy()
+    S, R = [], []
+    for i in range(6):
+        st, rw, trunc = env.step(torch.as_tensor(acts[:, i], device=env.sgs.device))
+        assert not bool(trunc.any())
+        S.append(st.cpu().numpy().copy()); R.append(rw.cpu().numpy().copy())
+    for e in range(B):
+        s = FakeSample([a.tolist() for a in acts[e, :6]] + [acts[e, 6].tolist()] * (epl - 6))
+        sgs = ke.environment(s, 256, gsz, M, 0.25, 1.0, epl, True, 42, dns)
+        assert np.array_equal(np.asarray(s.state0, dtype=np.float32), st0[e].astype(np.float32))
+        for i in range(6):
+            assert np.array_equal(np.asarray(s.states[i], dtype=np.float32), S[i][e].astype(np.float32)), (e, i)
+            assert float(s.rewards[i]) == float(R[i][e, 0]), (e, i)

@@ -35,7 +35,10 @@ def _worker(rank, ws, port, q, transport="nccl"):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
     try:
-        sb = mdist.ShardedBatch(B, _factory, transport=transport)
+        gather_to = None
+        if transport == "fused-learner":    # gather to rank 0 only: the other ranks publish but neither receive nor wait
+            transport, gather_to = "fused", 0
+        sb = mdist.ShardedBatch(B, _factory, transport=transport, gather_to=gather_to)
         a = _acts().cuda()
         for _ in range(3):
             gs, gr = sb.step_n(a, 10)
@@ -51,10 +54,10 @@ def _worker(rank, ws, port, q, transport="nccl"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused", "fused-ipc"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused", "fused-ipc", "fused-learner"])
 def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     import torch.multiprocessing as mp
-    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100, "fused-ipc": 150}[transport]
+    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100, "fused-ipc": 150, "fused-learner": 250}[transport]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q, transport)) for r in range(ws)]
@@ -69,8 +72,11 @@ def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     for _ in range(3):
         st, rw = env.step_n(a, 10)
     for o in outs:
-        assert np.array_equal(o[1], st.cpu().numpy())
-        assert np.array_equal(o[2], rw.cpu().numpy())
+        rows = slice(0, B)
+        if transport == "fused-learner" and o[0] != 0:      # a non-learner rank only holds its own rows
+            rows = slice(o[0] * B // ws, (o[0] + 1) * B // ws)
+        assert np.array_equal(o[1][rows], st.cpu().numpy()[rows])
+        assert np.array_equal(o[2][rows], rw.cpu().numpy()[rows])
 
 
 def test_peer_gather_single_rank_roundtrip():

@@ -149,3 +149,26 @@ def test_burger_batch_with_per_env_seeds_uses_device_tables_and_matches_single_e
         one.step_n(a[e:e + 1], 20)
         ref = one.u.cpu().numpy()
         assert np.max(np.abs(u[e] - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_masked_reset_keeps_per_env_counters_and_flags_the_host_scalars():
+    """IC(mask=...) resets a subset.  The device counters are per environment (the reset ones restart at 0, the
+    others keep running); the host scalars would describe neither, so history / checkpoint views refuse until a full reset."""
+    from marlpde_b200 import Burger
+    B, N = 6, 32
+    env = Burger(L=TWO_PI, N=N, dt=1e-3, nu=0.02, nsteps=40, case="turbulence", seed=42, nenvs=B, history=True)
+    env.step_n(None, 7, want_state=False, want_reward=False)
+    mask = np.array([1, 0, 0, 1, 0, 0], dtype=np.uint8)
+    env.IC(case="turbulence", mask=mask)
+    assert env.ioutnum_all.cpu().tolist() == [0, 7, 7, 0, 7, 7]
+    with pytest.raises(RuntimeError, match="masked reset"):
+        env.compute_Ek()
+    with pytest.raises(RuntimeError, match="masked reset"):
+        env.state_dict()
+    env.step_n(None, 3, want_state=False, want_reward=False)
+    assert env.ioutnum_all.cpu().tolist() == [3, 10, 10, 3, 10, 10]
+    fresh = Burger(L=TWO_PI, N=N, dt=1e-3, nu=0.02, nsteps=40, case="turbulence", seed=42, nenvs=1, history=False)
+    fresh.step_n(None, 3, want_state=False, want_reward=False)
+    assert torch.equal(env.v[0], fresh.v) and torch.equal(env.v[3], fresh.v)      # the reset rows restarted exactly
+    env.IC(case="turbulence")                                                       # a full reset clears the flag
+    env.compute_Ek()
