@@ -227,7 +227,7 @@ def workload_config(n_gpus):
                          f"nIntermediate={NSUB} solver steps per RL step; one step = one RL step of one batch"),
             "envs_per_gpu": B_PER_GPU, "N": N, "M": M, "n_intermediate": NSUB, "global_envs": B_PER_GPU * n_gpus,
             "l2": f"rotating pool of {POOL} independent batches per GPU (state working set > 126 MB L2)",
-            "parallelism": "single GPU" if n_gpus == 1 else f"env-sharded x{n_gpus}, state+reward rows gathered to every rank each RL step"}
+            "parallelism": "single GPU" if n_gpus == 1 else f"env-sharded x{n_gpus}, state+reward rows gathered to the learner rank each RL step"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -398,7 +398,10 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         return g_, n_k
 
-    chains = max(1, min(args.chains, pool, K))
+    # independent batches in flight inside the graph: 4 saturate the chip in steady state; a short run (K <= pool, every batch
+    # steps once) gains another 4 % from 10, which shortens the fill / drain of the pipeline (profiles/r2_lanes_chains.md)
+    want_chains = args.chains if args.chains > 0 else (10 if K <= pool else 4)
+    chains = max(1, min(want_chains, pool, K))
     if K > pool and pool % chains:
         chains = 1                          # a batch must stay on one chain (its launches are ordered by its stream)
     # every batch once outside any graph (module load, lazy set-up, first-use allocations)
@@ -677,7 +680,7 @@ def batch_sweep(torch, device):
     return out
 
 
-def other_configs(torch, device):
+def other_configs(torch, device, only=None):
     """BASELINE configs[2], [3], [4] on one GPU, measured in-process after the headline (each < 1 s of GPU time)."""
     from marlpde_b200 import Burger, KS
     peak, _ = peaks()
@@ -702,6 +705,8 @@ def other_configs(torch, device):
                               "alive": all(int((k.status != 0).sum()) == 0 for k in pool)}
     del pool
     torch.cuda.empty_cache()
+    if only == 'c3':
+        return res
     # ---- C4: Burgers DNS N=1024 x 512, 500 steps per launch, u / v / Ek history rows every step
     B, n, steps = 512, 1024, 500
     dns = Burger(L=L_DOM, N=n, dt=DT, nu=NU, nsteps=steps, case="turbulence", seed=100 + np.arange(B) % 4, nenvs=B, history=True,
@@ -761,9 +766,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the sweep / other-config / single-chain extras")
     ap.add_argument("--fused-single", action="store_true", help="diagnostic: bind the fused gather on one GPU")
-    ap.add_argument("--chains", type=int, default=4, help="independent batches in flight inside the replayed graph")
+    ap.add_argument("--chains", type=int, default=0, help="independent batches in flight inside the replayed graph (0 = auto: 4, or 10 for a run of K <= pool steps)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per environment (0 = library default)")
-    ap.add_argument("--gather", default="all", choices=["all", "learner"],
+    ap.add_argument("--gather", default="learner", choices=["all", "learner"],
                     help="multi-GPU: rows gathered to every rank (all-gather) or to rank 0 only (SURVEY 8e: gather semantics suffice)")
     ap.add_argument("--rewards-only", action="store_true", help="multi-GPU: gather only the rewards (configs[4] wording)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c5: BASELINE configs[4] per GPU (MARL, 8192 envs)")

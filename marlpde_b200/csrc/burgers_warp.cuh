@@ -447,10 +447,8 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 v[p] = cx<T>(X[p].re * invN, X[p].im * invN);
-                bad |= blown(v[p]);
             }
             vN = cx<T>(XN * invN, T(0));
-            if (f.dc) bad |= blown(vN);
             iout += 1;
           } else {
             // nonlinear term X = fft(u^2 / 2) (Burger.py:487); with eddy-viscosity actions the forcing
@@ -542,7 +540,6 @@ struct BurgersWarp {
                 v[p] = cx<T>(fma(cF[p], F.re, fma(cfo[p], fma(T(-3), fnn.re, fn[p].re), cv[p] * v[p].re)),
                              fma(cF[p], F.im, fma(cfo[p], fma(T(-3), fnn.im, fn[p].im), cv[p] * v[p].im)));
                 fn[p] = fnn;
-                bad |= blown(v[p]);
             }
             {   // k = 0: Fn = 0, F real -> Im v[0] is a constant of the motion; Nyquist: F real, Fn imaginary
                 const T cvN = stash[0], cfoN = stash[1], cFN = stash[2];
@@ -550,10 +547,7 @@ struct BurgersWarp {
                 const T FN = q1 ? (T)__fmul_rn(dtf, (float)FhN) : FhN;
                 vN = cx<T>(fma(cFN, FN, cvN * vN.re), fma(cfoN, fma(T(-3), fnnN, fnN), cvN * vN.im));
                 fnN = fnnN;
-                if (f.dc) {
-                    v[0].im = v0im;
-                    bad |= blown(vN);
-                }
+                if (f.dc) v[0].im = v0im;
             }
             iout += 1;
 
@@ -561,11 +555,20 @@ struct BurgersWarp {
             f.inv(v, vN.re, U);
           }
 
-            // float32 spectrum chain (Q6): Ek row from complex64(v), sequential float32 sum
+            // float32 spectrum chain (Q6): Ek row from complex64(v), sequential float32 sum.  The same cast is where the
+            // reference detects a blow-up (`vv[i] = v` overflows complex64 with np.seterr(over='raise'), Burger.py:8,498):
+            // a component that is inf / nan AFTER the cast marks the environment -- checked on the FP32 pipe
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                acc32[p] = __fadd_rn(acc32[p], ek_row_f32((float)v[p].re, (float)v[p].im, N, dxf));
-            accN = __fadd_rn(accN, ek_row_f32((float)vN.re, (float)vN.im, N, dxf));
+            for (int p = 0; p < P; ++p) {
+                const float fre = (float)v[p].re, fim = (float)v[p].im;
+                bad |= !(fabsf(fre) <= FLT_MAX && fabsf(fim) <= FLT_MAX);
+                acc32[p] = __fadd_rn(acc32[p], ek_row_f32(fre, fim, N, dxf));
+            }
+            {
+                const float fre = (float)vN.re, fim = (float)vN.im;
+                if (f.dc) bad |= !(fabsf(fre) <= FLT_MAX && fabsf(fim) <= FLT_MAX);
+                accN = __fadd_rn(accN, ek_row_f32(fre, fim, N, dxf));
+            }
 
             if (hist) {
                 // blow-up semantics: rows are only written while the env is healthy

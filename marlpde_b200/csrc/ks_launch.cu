@@ -14,10 +14,11 @@ __global__ void __launch_bounds__(64, MINB) ks_warp_kernel(const SpectralParams<
 
 template <typename T, int N, int TS, int MINB = 1>
 static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
-    constexpr int TPW = 32 / TS;
+    using K = KSWarp<T, N, TS>;
+    constexpr int TPW = K::TPW;
     const int64_t warps = (p.B + TPW - 1) / TPW;
-    const int scr = p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2;
-    const size_t smem = ((size_t)2 * TPW * scr + 7 * (N / 2 + 1)) * sizeof(T);      // team scratch + shared ETDRK4 tables
+    const int scr = 2 * K::R::SMEM_CX + (p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2);
+    const size_t smem = ((size_t)2 * TPW * scr + 7 * (N / 2 + 1)) * sizeof(T);      // team areas + shared ETDRK4 tables
     // programmatic dependent launch, as for the Burgers kernels (the kernel reads mutable state after pdl_wait())
     static const bool pdl = [] { const char* s = std::getenv("MPDE_PDL"); return !(s && s[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
@@ -36,10 +37,10 @@ static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
 
 // lanes per environment for N = 64: mpde_config.team_lanes, else MPDE_KS_TS (tuning), else the default
 static int ks_team(int requested, int dflt) {
-    if (requested == 8 || requested == 16 || requested == 32) return requested;
+    if (requested == 8 || requested == 16 || requested == 32 || requested == -8) return requested;
     if (const char* s = std::getenv("MPDE_KS_TS")) {
         const int v = std::atoi(s);
-        if (v == 8 || v == 16 || v == 32) return v;
+        if (v == 8 || v == 16 || v == 32 || v == -8) return v;
     }
     return dflt;
 }
@@ -47,8 +48,17 @@ static int ks_team(int requested, int dflt) {
 template <typename T>
 int launch_ks(const SpectralParams<T>& p, cudaStream_t st) {
     if (p.N == 64) {
-        switch (ks_team(p.team_lanes, 16)) {       // B200, 8192 envs, 10 steps: 32 lanes 122 us, 16 lanes 106 us, 8 lanes 109 us
+        // B200, 8192 envs, 10 steps per launch: 32 lanes 122 us, 16 lanes 102.6 us, 8 lanes (radix-2 shuffles) 109 us,
+        // 8 lanes with the transposed 4 x (2 x 4) transform (-8, default from round 2) 88.9 us
+        switch (ks_team(p.team_lanes, -8)) {
             case 8: return launch_ks_warp<T, 64, 8>(p, st);
+            case -8: {      // 8 lanes, transposed 4 x (2 x 4) transform (WarpFFT<T,32,-8>)
+                int minb = 4;
+                if (const char* s = std::getenv("MPDE_KS_MINB")) minb = std::atoi(s);
+                if (minb == 6) return launch_ks_warp<T, 64, -8, 6>(p, st);
+                if (minb == 5) return launch_ks_warp<T, 64, -8, 5>(p, st);
+                return launch_ks_warp<T, 64, -8, 4>(p, st);
+            }
             case 32: return launch_ks_warp<T, 64, 32>(p, st);
             default: {      // B200, 8192 envs, 10 steps: 236 regs 108.8 us, 168 regs 110.9 us, 128 regs (some spills) 99.5 us
                 int minb = 8;

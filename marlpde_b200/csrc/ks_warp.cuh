@@ -32,7 +32,9 @@ struct KSWarp {
         // (read from shared memory at each use instead of living in 7 P registers per lane: fewer registers, more
         // resident warps, fewer waves)
         constexpr int TW = H + 1;
-        T* const tab = smem + (size_t)wpc * TPW * max(prm.M, 2 * N + N / 2);
+        // per team: [FFT exchange area (transposed transforms only) | scratch]; then the shared tables
+        const int scr_team = 2 * R::SMEM_CX + max(prm.M, 2 * N + N / 2);
+        T* const tab = smem + (size_t)wpc * TPW * scr_team;
         for (int i = threadIdx.x; i < 7 * TW; i += blockDim.x) {
             const int t = i / TW, k = i - t * TW;
             tab[i] = t < 6 ? prm.etd[t * N + k] : T(-0.5) * prm.kwave[k];
@@ -40,16 +42,16 @@ struct KSWarp {
         __syncthreads();
         const int64_t first = ((int64_t)blockIdx.x * wpc + warp) * TPW;
         if (first >= prm.B) return;
-        R f;
-        f.init(prm.tw);
-        const int tl = f.c.tl;
         const int team = lane / TS;
+        T* const team_smem = smem + (size_t)(warp * TPW + team) * scr_team;
+        R f;
+        f.init(prm.tw, reinterpret_cast<Cx<T>*>(team_smem));
+        const int tl = f.c.tl;
         const int64_t e = first + team;
         const bool has = e < prm.B;
         const int64_t ec = has ? e : 0;
         const int flags = prm.flags;
-        const int scr = max(prm.M, 2 * N + N / 2);
-        T* scratch = smem + (size_t)(warp * TPW + team) * scr;
+        T* scratch = team_smem + 2 * R::SMEM_CX;
         const T dt = prm.dt, invN = T(1) / T(N);
 
         int kk[P];

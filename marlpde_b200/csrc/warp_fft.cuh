@@ -398,6 +398,93 @@ struct WarpFFT<T, 16, -8, TWS> {
     __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[2], int q) const { return shfl(z[q], part[q], tmask); }
 };
 
+// 32 points on 8 lanes x 4 registers as 4 x (2 x 4): a 4-point transform in registers, the twiddle W32^(lane r), ONE
+// transpose through shared memory (row stride 9 complex words: conflict-free), a radix-2 stage between lanes l and l ^ 4,
+// the twiddle W8^(m h) and a second 4-point transform in registers.  Natural order in and out: point j = 8 p + tl in
+// register p, wavenumber k = tl + 8 q in register q.  Per environment 8 x 64 = 512 FP64 and 128 SHFL.32 instructions
+// instead of 16 x 56 = 896 and 512 for the 16-lane radix-2 shuffle network: the KS step is nine of these transforms.
+// Selected with the team-size tag -8 for H = 32 (N = 64).
+template <typename T, int TWS>
+struct WarpFFT<T, 32, -8, TWS> {
+    static constexpr int H = 32, TS = 8, P = 4, ROW = 9;
+    static constexpr int SMEM_CX = 4 * ROW;
+    int tl, base, k1, hbit;
+    unsigned tmask;
+    T sg;
+    Cx<T> w1[3];                        // W32^(tl r), r = 1..3
+    Cx<T> w2[3];                        // W8^(m h),  m = 1..3 (1 on the lanes with h = 0)
+    Cx<T>* sm;
+
+    __device__ __forceinline__ static int kidx(int p, int t) { return t + 8 * p; }
+    // table entry exp(-2 pi i m / 32) from tw[j] = exp(-2 pi i j / (32 TWS)), j < 32 (TWS = 2): W32^m = tw[2 m], m < 32
+    __device__ __forceinline__ static Cx<T> w32(const Cx<T>* __restrict__ tw, int m) {
+        const int j = m * TWS;                                   // j < 32 TWS
+        const Cx<T> w = ldcx(tw + (j & 31));
+        return (j & 32) ? cx<T>(-w.re, -w.im) : w;               // exp(-2 pi i (j + 32) / 64) = -exp(-2 pi i j / 64)
+    }
+    __device__ __forceinline__ void init(const Cx<T>* __restrict__ tw, Cx<T>* team_smem) {
+        static_assert(TWS == 2, "the 32-point transposed transform reads the N = 64 twiddle table");
+        const int lane = threadIdx.x & 31;
+        tl = lane & 7;
+        base = lane & ~7;
+        tmask = 0xffu << base;
+        k1 = tl & 3;
+        hbit = tl >> 2;
+        sg = hbit ? T(-1) : T(1);
+        sm = team_smem;
+#pragma unroll
+        for (int r = 1; r < 4; ++r) {
+            w1[r - 1] = w32(tw, tl * r);                         // tl r <= 21
+            w2[r - 1] = hbit ? w32(tw, 4 * r) : cx<T>(T(1), T(0));   // W8^r = W32^(4 r)
+        }
+    }
+    using Q = WarpFFT<T, 16, 4, TWS>;                            // its dft4 is the natural-order 4-point transform
+    __device__ __forceinline__ void fwd(Cx<T> (&z)[4]) const {
+        Q::template dft4<false>(z);                              // over p -> k1 in registers
+#pragma unroll
+        for (int r = 1; r < 4; ++r) z[r] = cmul(z[r], w1[r - 1]);
+        __syncwarp(tmask);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) stcx(sm + r * ROW + tl, z[r]);
+        __syncwarp(tmask);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) z[m] = ldcx(sm + k1 * ROW + 4 * hbit + m);      // lane (k1, h): points n2 = 4 h + m
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const Cx<T> o = shfl_xor(z[m], 4, tmask);
+            z[m] = cx<T>(fma(sg, z[m].re, o.re), fma(sg, z[m].im, o.im));
+        }
+#pragma unroll
+        for (int m = 1; m < 4; ++m) z[m] = cmul(z[m], w2[m - 1]);
+        Q::template dft4<false>(z);                              // over m -> q: k = k1 + 4 h + 8 q
+    }
+    __device__ __forceinline__ void inv(Cx<T> (&z)[4]) const {
+        Q::template dft4<true>(z);
+#pragma unroll
+        for (int m = 1; m < 4; ++m) z[m] = cmulc(z[m], w2[m - 1]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const Cx<T> o = shfl_xor(z[m], 4, tmask);
+            z[m] = cx<T>(fma(sg, z[m].re, o.re), fma(sg, z[m].im, o.im));
+        }
+        __syncwarp(tmask);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) stcx(sm + k1 * ROW + 4 * hbit + m, z[m]);
+        __syncwarp(tmask);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) z[r] = ldcx(sm + r * ROW + tl);
+#pragma unroll
+        for (int r = 1; r < 4; ++r) z[r] = cmulc(z[r], w1[r - 1]);
+        Q::template dft4<true>(z);
+    }
+    __device__ __forceinline__ void fwd2(Cx<T> (&za)[4], Cx<T> (&zb)[4]) const { fwd(za); fwd(zb); }
+    // value held for wavenumber -k (mod 32): k = tl + 8 q -> lane (8 - tl) & 7, register 3 - q (tl > 0) or (4 - q) & 3
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[4], int q) const {
+        const Cx<T> far = shfl(z[3 - q], base + ((8 - tl) & 7), tmask);
+        return tl == 0 ? z[(4 - q) & 3] : far;
+    }
+};
+
 template <typename T, int N, int TS_ = (N / 2 < 32 ? N / 2 : 32)>      // TS_ < 0: tag of an alternative transform with |TS_| lanes
 struct RealFFT {
     static constexpr int H = N / 2;
