@@ -272,7 +272,10 @@ class Burger(SpectralEnv):
         self._truth_shift = key
 
     def _upload_forcing(self):
-        if not self.forcing or not self._forcing_dirty:
+        if not self.forcing:
+            self._forcing_dirty = False
+            return
+        if not self._forcing_dirty:
             return
         coef = forcing_spectrum_coefficients(self._randfac1, self._randfac2, self._offset, self.L, self.dt,
                                              self.stepper, self.N, self.nenvs)
@@ -307,15 +310,23 @@ class Burger(SpectralEnv):
         """``n`` solver steps with the same actions (the inner loop of
         burger_environment.py:148-155) + getState + reward, as ONE kernel launch.
         Returns (state [B,S], reward [B,A]) device tensors (None when not requested)."""
-        self._upload_forcing()
+        if self._forcing_dirty:
+            self._upload_forcing()
         a = self._actions(actions)
         st = self._state_buf if want_state else None
         rw = self._reward_buf if (want_reward and (self._spec_ref is not None or self._truth_shift is not None)) else None
-        L_check(self._lib.mpde_step(self._h, self._ptr(a), int(n), self._ptr(st), self._ptr(rw), self._stream()))
+        # raw addresses (ctypes converts ints to void*): this call sits on the host path of every RL step
+        rc = self._lib.mpde_step(self._h, a.data_ptr() if a is not None else None, int(n),
+                                 st.data_ptr() if st is not None else None, rw.data_ptr() if rw is not None else None,
+                                 torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            L_check(rc)
         self.stepnum += n
         self.ioutnum += n
+        t, dt = self.t, self.dt
         for _ in range(n):
-            self.t += self.dt                                              # Burger.py:494
+            t += dt                                                        # Burger.py:494 (accumulated, not n * dt)
+        self.t = t
         if st is not None:
             self._state_at = self.ioutnum
         if rw is not None:

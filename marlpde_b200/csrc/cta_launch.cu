@@ -33,10 +33,10 @@ static int launch_cta(const SpectralParams<T>& p, cudaStream_t st) {
 }
 
 // N = 1024 Burgers DNS (no actions / closures / state / reward): one warp per environment, state in registers (dns_warp.cuh)
-template <typename T>
+template <typename T, bool VS>
 __global__ void __launch_bounds__(32) burgers_dns1024_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Dns1024<T>::run(prm, smem_raw);
+    Dns1024<T, VS>::run(prm, smem_raw);
 }
 template <typename T>
 static bool dns_warp_eligible(const SpectralParams<T>& p) {
@@ -45,8 +45,10 @@ static bool dns_warp_eligible(const SpectralParams<T>& p) {
 }
 template <typename T>
 static int launch_dns1024(const SpectralParams<T>& p, cudaStream_t st) {
-    const size_t smem = Dns1024<T>::smem_bytes();
-    burgers_dns1024_kernel<T><<<(unsigned)p.B, 32, smem, st>>>(p);
+    // MPDE_DNS_VREG=1: spectrum in registers (first version of the kernel) instead of shared memory
+    static const bool vreg = [] { const char* s = std::getenv("MPDE_DNS_VREG"); return s && s[0] == '1'; }();
+    if (vreg) burgers_dns1024_kernel<T, false><<<(unsigned)p.B, 32, Dns1024<T, false>::smem_bytes(), st>>>(p);
+    else burgers_dns1024_kernel<T, true><<<(unsigned)p.B, 32, Dns1024<T, true>::smem_bytes(), st>>>(p);
     return 1;
 }
 

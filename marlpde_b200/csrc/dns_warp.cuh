@@ -21,7 +21,9 @@
 
 namespace mpde {
 
-template <typename T>
+// VS: keep the spectrum v in shared memory instead of 64 registers (the Hermitian partner is then a second shared-memory
+// read instead of a shuffle): no spills and more scheduling freedom for the transforms, +128 LSU cycles per step
+template <typename T, bool VS = true>
 struct Dns1024 {
     static constexpr int N = 1024, H = 512, NH = 513;
     static constexpr int ROW = 33;                       // exchange-buffer row stride (complex words): conflict-free transposes
@@ -29,7 +31,7 @@ struct Dns1024 {
     // acc (float) 513; entry 512 of the last three tables and FN[513] (= v[N/2]) belong to the Nyquist mode, which lane 0
     // updates out of shared memory.  Fn_old is touched once per step, so it lives here instead of in 64 more registers (v, the work
     // array and their temporaries already fill the 255-register budget).
-    static constexpr int CX_WORDS = 16 * ROW + 512 + 32 + 514 + 514;
+    static constexpr int CX_WORDS = 16 * ROW + 512 + 32 + 514 + 514 + (VS ? 512 : 0);
     static size_t smem_bytes() { return sizeof(Cx<T>) * CX_WORDS + sizeof(float) * 516; }
 
     // ---- 16-point transform in registers, natural order in and out ---------------------------------------------
@@ -134,7 +136,8 @@ struct Dns1024 {
         Cx<T>* T2 = T1 + 512;
         Cx<T>* CC = T2 + 32;
         Cx<T>* FN = CC + 514;
-        float* acc = reinterpret_cast<float*>(FN + 514);
+        Cx<T>* V = FN + 514;                              // VS only: v[k], natural order
+        float* acc = reinterpret_cast<float*>(V + (VS ? 512 : 0));
         const int flags = prm.flags;
         const T dt = prm.dt, invN = T(1) / T(N);
         const T nu = prm.nu[e];
@@ -175,27 +178,33 @@ struct Dns1024 {
         bool live = was_live, bad = false;
         int iout = prm.iout[e];
         T tnow = prm.tnow[e];
-        Cx<T> v[16], z[16];
+        Cx<T> v[VS ? 1 : 16], z[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            v[r] = ldcx(prm.v + e * NH + 32 * r + lane);
+            const Cx<T> t = ldcx(prm.v + e * NH + 32 * r + lane);
+            if constexpr (VS) V[32 * r + lane] = t; else v[r] = t;
             FN[32 * r + lane] = ldcx(prm.fn + e * NH + 32 * r + lane);
         }
         __syncwarp();
+        auto vget = [&](int r) { if constexpr (VS) return ldcx(V + 32 * r + lane); else return v[r]; };
+        auto vmirror = [&](int r) {
+            if constexpr (VS) return ldcx(V + ((512 - 32 * r - lane) & 511));
+            else return mirror(v, r, lane);
+        };
 
         // pre-processing of the inverse real transform + inverse: z = N Re ifft(v) as pairs (x_2j, x_2j+1)
         auto to_real = [&]() {
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const Cx<T> wk = cmul(wbase, w32(r));
-                const Cx<T> vm = mirror(v, r, lane);
-                const Cx<T> Ee = cx<T>(v[r].re + vm.re, v[r].im - vm.im);
-                const Cx<T> Dd = cx<T>(v[r].re - vm.re, v[r].im + vm.im);
+                const Cx<T> vr = vget(r), vm = vmirror(r);
+                const Cx<T> Ee = cx<T>(vr.re + vm.re, vr.im - vm.im);
+                const Cx<T> Dd = cx<T>(vr.re - vm.re, vr.im + vm.im);
                 z[r] = cx<T>(fma(-Dd.im, wk.re, fma(Dd.re, wk.im, Ee.re)), fma(Dd.re, wk.re, fma(Dd.im, wk.im, Ee.im)));
             }
             {   // k = 0 (lane 0, register 0): only Re v[0], Re v[N/2] enter (selects, no branch: the warp stays converged)
-                const T vNre = FN[H + 1].re;
-                const Cx<T> dc = cx<T>(v[0].re + vNre, v[0].re - vNre);
+                const T vNre = FN[H + 1].re, v0re = vget(0).re;
+                const Cx<T> dc = cx<T>(v0re + vNre, v0re - vNre);
                 z[0] = lane == 0 ? dc : z[0];
             }
             fft512<true>(z, E, T1, T2, lane);
@@ -217,6 +226,7 @@ struct Dns1024 {
             fft512<false>(z, E, T1, T2, lane);
             const T XN = ((z[0].re - z[0].im)) * (T(2) * hs);      // lane 0: fft(u^2/2)[N/2] (real)
             // ---- ABCN update (Burger.py:486-489) ------------------------------------------------------------------
+            float fre[16], fim[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const Cx<T> wk = cmul(wbase, w32(r));
@@ -228,8 +238,9 @@ struct Dns1024 {
                 const Cx<T> fnn = cx<T>(-kwr * X.im, kwr * X.re);
                 const Cx<T> c = ldcx(CC + 32 * r + lane);                                  // (cv, cfo)
                 const Cx<T> fo = ldcx(FN + 32 * r + lane);
-                Cx<T> vn = cx<T>(fma(c.im, fma(T(-3), fnn.re, fo.re), c.re * v[r].re),
-                                 fma(c.im, fma(T(-3), fnn.im, fo.im), c.re * v[r].im));
+                const Cx<T> vo = vget(r);
+                Cx<T> vn = cx<T>(fma(c.im, fma(T(-3), fnn.re, fo.re), c.re * vo.re),
+                                 fma(c.im, fma(T(-3), fnn.im, fo.im), c.re * vo.im));
                 if (r == 0 && forcing) {
                     // 3-mode forcing (Burger.py:410-421) on k = 1, 2, 3 = lanes 1..3: dt F / (1 + C) = 2 cfo F (other lanes: weight 0)
                     const int m = lane - 1 < 0 ? 0 : (lane - 1 > 2 ? 2 : lane - 1);
@@ -237,7 +248,9 @@ struct Dns1024 {
                     const T wgt = (lane >= 1 && lane <= 3) ? T(2) * c.im : T(0);
                     vn = cx<T>(fma(wgt, F.re, vn.re), fma(wgt, F.im, vn.im));
                 }
-                v[r] = vn;
+                if constexpr (VS) stcx(V + 32 * r + lane, vn); else v[r] = vn;
+                fre[r] = (float)vn.re;
+                fim[r] = (float)vn.im;
                 stcx(FN + 32 * r + lane, fnn);
             }
             iout += 1;
@@ -258,11 +271,8 @@ struct Dns1024 {
             // ---- float32 spectrum chain (Q6) + blow-up detection on the complex64 cast (Burger.py:498) -------------
             const bool write_hist = prm.hist_rows > 0 && iout < prm.hist_rows;
             const int64_t hrow = e * prm.hist_rows + iout;
-            float fre[16], fim[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                fre[r] = (float)v[r].re;
-                fim[r] = (float)v[r].im;
                 bad |= !(fabsf(fre[r]) <= FLT_MAX && fabsf(fim[r]) <= FLT_MAX);
                 const float a = __fadd_rn(acc[32 * r + lane], ek_row_f32(fre[r], fim[r], N, dxf));
                 acc[32 * r + lane] = a;
@@ -310,7 +320,7 @@ struct Dns1024 {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const int k = 32 * r + lane;
-                    stcx(prm.v + e * NH + k, v[r]);
+                    stcx(prm.v + e * NH + k, vget(r));
                     stcx(prm.fn + e * NH + k, FN[k]);
                 }
                 if (lane == 0) {

@@ -18,6 +18,11 @@ class HostPipeline:
         dev, dt = e0.device, e0.dtype
         B, M, S, A = e0.nenvs, e0.M, e0._state_buf.shape[1], e0._reward_buf.shape[1]
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.envs]
+        # whatever set the environments up (IC / reset kernels, table uploads) ran on the caller's current stream: order every
+        # slot stream behind it before the first submit
+        cur = torch.cuda.current_stream(dev)
+        for st_ in self.streams:
+            st_.wait_stream(cur)
         self.done = [torch.cuda.Event() for _ in self.envs]
         self.act_host = [torch.empty((B, M), dtype=dt).pin_memory() for _ in self.envs]
         self.act_dev = [torch.empty((B, M), dtype=dt, device=dev) for _ in self.envs]
