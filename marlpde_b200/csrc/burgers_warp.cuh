@@ -94,10 +94,10 @@ struct BurgersWarp {
 
     // Dynamic Smagorinsky closure (Burger.py:357-399 = Burger_fd.py:358-411): Germano identity with a sharp spectral test
     // filter |k| > N//4 that the reference applies IN PLACE to the state v (quirk Q4; in Burger_fd v is refreshed from u at
-    // the end of the step, so the filter has no lasting effect there).  X = unscaled fft(U^2), U = N u.
+    // the end of the step, so the filter has no lasting effect there).  xscale X = fft(u^2) (X comes from U = N u).
     __device__ __forceinline__ static void dsm_sgs(const R& f, const Cx<T> (&X)[P], T XN, Cx<T> (&v)[P], Cx<T>& vN, const T (&kw)[P],
                                                    T kwN, const Cx<T> (&ws1)[P], const Cx<T> (&dudx)[P], const Cx<T> (&d2)[P],
-                                                   T scale_nl, T invN, T inv_dx, Cx<T> (&sgs)[P]) {
+                                                   T xscale, T invN, T inv_dx, Cx<T> (&sgs)[P]) {
         Cx<T> z[P];
         // dynamic Smagorinsky, Burger.py:357-399 (Germano identity with a sharp spectral
         // test filter |k| > N//4 applied IN PLACE to the state v, :369-370)
@@ -108,9 +108,9 @@ struct BurgersWarp {
         const bool cutN = fabs(kwN) > T(N / 4);
         Cx<T> w[P], L1[P], uh[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p)      // filtered fft(u^2) = 2 X
-            w[p] = cut[p] ? cx<T>(0, 0) : cx<T>((T(2) * scale_nl) * X[p].re, (T(2) * scale_nl) * X[p].im);
-        f.inv(w, cutN ? T(0) : (T(2) * scale_nl) * XN, L1);
+        for (int p = 0; p < P; ++p)      // filtered fft(u^2) = xscale X
+            w[p] = cut[p] ? cx<T>(0, 0) : cx<T>(xscale * X[p].re, xscale * X[p].im);
+        f.inv(w, cutN ? T(0) : xscale * XN, L1);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             L1[p] = cx<T>(L1[p].re * (T(0.5) * invN), L1[p].im * (T(0.5) * invN));
@@ -264,9 +264,10 @@ struct BurgersWarp {
         // u is kept as U = N u in registers and the transforms are unscaled: the factor 1/(2 N^2) of
         // fft(u^2 / 2) is folded into the wavenumber that multiplies it (Fn = i k X)
         const T scale_nl = T(0.5) * invN * invN;
+        // the nonlinear term comes out of the UNSCALED split step (X2 = 2 fft(U^2)): its 1/2 is folded in here as well
         T kws[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) kws[p] = kw[p] * scale_nl;
+        for (int p = 0; p < P; ++p) kws[p] = kw[p] * (T(0.5) * scale_nl);
         {
             const T CN = T(0.5) * (kwN * kwN) * nu * dt;
             const T rN = T(1) / (T(1) + CN);
@@ -274,7 +275,7 @@ struct BurgersWarp {
                 stash[0] = (T(1) - CN) * rN;          // cvN
                 stash[1] = T(0.5) * dt * rN;          // cfoN
                 stash[2] = q1 ? rN : dt * rN;         // cFN
-                stash[3] = kwN * scale_nl;            // kwN (scaled)
+                stash[3] = kwN * (T(0.5) * scale_nl); // kwN (scaled)
             }
         }
         Cx<T> ws1[P];
@@ -339,22 +340,25 @@ struct BurgersWarp {
 #pragma unroll
                 for (int p = 0; p < P; ++p) z[p] = fa[p];
                 f.fwd(z, Fa, FaN, T(1), ws1);
-            } else {                          // eddy viscosity: fold 1/dx^2 and the 1/N of U once
-                const T s = invN / (prm.dx * prm.dx);
+            } else {                          // eddy viscosity: fold 1/dx^2, the 1/N of U and the 1/2 of the raw split step once
+                // (Burger_fd applies the field in real space: no split step, no 1/2)
+                const T s = (fd ? T(1) : T(0.5)) * invN / (prm.dx * prm.dx);
 #pragma unroll
                 for (int p = 0; p < P; ++p) fa[p] = cx<T>(fa[p].re * s, fa[p].im * s);
             }
         }
 
         // ---- stochastic forcing spectrum (Burger.py:410-421): non-zero at k = 1,2,3 only ----------
-        Cx<T> Fc[P];
+        // natural-order layouts (k = tl + TS p, TS >= 4) hold k = 1, 2, 3 in register 0 only: one complex register instead of P
+        constexpr int FP = (R::C::NATURAL && TS >= 4) ? 1 : P;
+        Cx<T> Fc[FP];
 #pragma unroll
-        for (int p = 0; p < P; ++p) Fc[p] = cx<T>(0, 0);
+        for (int p = 0; p < FP; ++p) Fc[p] = cx<T>(0, 0);
         const Cx<T>* fc_row = prm.fcoef + ((flags & F_FORCING_PER_ENV) ? ec : 0) * prm.stepper * 3;
         int col = (flags & F_FORCING) ? iout % prm.stepper : 0;      // column ioutnum % stepper (Q3)
         if ((flags & F_FORCING) && prm.stepper == 1) {
 #pragma unroll
-            for (int p = 0; p < P; ++p)
+            for (int p = 0; p < FP; ++p)
                 if (kk[p] >= 1 && kk[p] <= 3) Fc[p] = ldcx(fc_row + (kk[p] - 1));
         }
 
@@ -403,7 +407,7 @@ struct BurgersWarp {
                     zz[p] = cx<T>(U[p].re * U[p].re, U[p].im * U[p].im);
                 }
                 f.fwd(zz, X2, X2N, T(1), ws1);
-                dsm_sgs(f, X2, X2N, v, vN, kw, kwN, ws1, dudx_c, d2_c, scale_nl, invN, inv_dx, sgs_d);
+                dsm_sgs(f, X2, X2N, v, vN, kw, kwN, ws1, dudx_c, d2_c, T(2) * scale_nl, invN, inv_dx, sgs_d);
             }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -466,9 +470,9 @@ struct BurgersWarp {
                 for (int p = 0; p < P; ++p)
                     zf[p] = cx<T>(fa[p].re * (left[p] - T(2) * U[p].re + U[p].im),
                                   fa[p].im * (U[p].re - T(2) * U[p].im + right[p]));
-                f.fwd2(z, X, XN, T(1), ws1, zf, S, SN, T(1), ws1);
+                f.fwd2_raw(z, X, XN, zf, S, SN);          // X = 2 fft(U^2); S = fft of the forcing (its input carries the 1/2)
             } else {
-                f.fwd(z, X, XN, T(1), ws1);
+                f.fwd_raw(z, X, XN);
             }
 
             Cx<T> Fh[P];
@@ -493,7 +497,7 @@ struct BurgersWarp {
                     for (int p = 0; p < P; ++p)
                         sgs[p] = cx<T>(cd2 * fabs(dudx[p].re) * d2[p].re, cd2 * fabs(dudx[p].im) * d2[p].im);
                 } else {
-                    dsm_sgs(f, X, XN, v, vN, kw, kwN, ws1, dudx, d2, scale_nl, invN, inv_dx, sgs);
+                    dsm_sgs(f, X, XN, v, vN, kw, kwN, ws1, dudx, d2, scale_nl, invN, inv_dx, sgs);      // X = 2 fft(U^2)
                 }
                 Cx<T> G[P];
                 T GN;
@@ -507,12 +511,12 @@ struct BurgersWarp {
                 // the forcing spectrum REPLACES whatever the closures accumulated (Q2)
                 if (multi_col) {
 #pragma unroll
-                    for (int p = 0; p < P; ++p)
+                    for (int p = 0; p < FP; ++p)
                         if (kk[p] >= 1 && kk[p] <= 3) Fc[p] = ldcx(fc_row + col * 3 + (kk[p] - 1));
                     col = (col + 1 == prm.stepper) ? 0 : col + 1;
                 }
 #pragma unroll
-                for (int p = 0; p < P; ++p) Fh[p] = Fc[p];
+                for (int p = 0; p < P; ++p) Fh[p] = p < FP ? Fc[p] : cx<T>(0, 0);
                 FhN = T(0);
             }
 
@@ -651,36 +655,45 @@ struct BurgersWarp {
             T left[P], right[P];
             halo(f, U, left, right);
             const T sd2 = inv_dx2 * invN, sdt = invN / dt;
-            if (has) {
-                const int64_t off = e * (ver == 0 ? N : 2 * N);
-                const Cx<T> ii = cx<T>(inf, inf);
-                // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
-                auto put = [&](int64_t idx, Cx<T> val) {
-                    if (prm.peer.mc_state) {      // one multicast store reaches every rank's buffer (this one included)
-                        st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + idx, val);
-                        return;
-                    }
-                    stcx(reinterpret_cast<Cx<T>*>(state_out + off) + idx, val);
-                    for (int q = 0; q < prm.peer.n_data; ++q)
-                        stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + idx, val);
-                };
+            // Stage this team's row in its scratch area; then the WARP writes whole rows: 16 consecutive lanes cover 256
+            // contiguous bytes of one environment's row.  (A 4-lane team by itself covers 64 bytes per store instruction: fine
+            // for HBM, but in the fused gather those stores travel over NVLink, whose write efficiency follows the size of
+            // the contiguous segment: 8 GPUs reached 0.55 TB/s of ingress with 64-byte segments.)
+            const int rl_shift = ilog2(H) + (ver == 0 ? 0 : 1);        // complex words per state row = 1 << rl_shift
+            Cx<T>* const stage = reinterpret_cast<Cx<T>*>(scratch);
+            const Cx<T> ii = cx<T>(inf, inf);
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const int j = p * TS + tl;
-                    const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
-                    const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2, (U[p].re - T(2) * U[p].im + right[p]) * sd2);
-                    if (ver == 0) {
-                        put(j, live ? d2 : ii);
-                    } else if (ver == 1) {
-                        const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
-                        put(j, live ? dudt : ii);
-                        put(H + j, live ? d2 : ii);
-                    } else {
-                        put(j, live ? u : ii);
-                        put(H + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
-                    }
+            for (int p = 0; p < P; ++p) {
+                const int j = p * TS + tl;
+                const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
+                const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2, (U[p].re - T(2) * U[p].im + right[p]) * sd2);
+                if (ver == 0) {
+                    stcx(stage + j, live ? d2 : ii);
+                } else if (ver == 1) {
+                    const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
+                    stcx(stage + j, live ? dudt : ii);
+                    stcx(stage + H + j, live ? d2 : ii);
+                } else {
+                    stcx(stage + j, live ? u : ii);
+                    stcx(stage + H + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
                 }
             }
+            __syncwarp();                   // the whole warp: every lane is here (mode flags and trip counts are warp-uniform)
+            for (int idx = lane; idx < (TPW << rl_shift); idx += 32) {
+                const int t = idx >> rl_shift, c = idx & ((1 << rl_shift) - 1);
+                if (first + t >= prm.B) continue;
+                const Cx<T> val = ldcx(reinterpret_cast<const Cx<T>*>(smem + (size_t)(warp * TPW + t) * scr + 2 * R::SMEM_CX) + c);
+                const int64_t off = (first + t) * ((int64_t)2 << rl_shift);         // row start, in T
+                // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
+                if (prm.peer.mc_state) {      // one multicast store reaches every rank's buffer (this one included)
+                    st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + c, val);
+                } else {
+                    stcx(reinterpret_cast<Cx<T>*>(state_out + off) + c, val);
+                    for (int q = 0; q < prm.peer.n_data; ++q)
+                        stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + c, val);
+                }
+            }
+            __syncwarp();
         } else if (!HOT && prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store

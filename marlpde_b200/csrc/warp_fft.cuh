@@ -32,6 +32,7 @@ struct WarpFFT {
     static constexpr int TS = TS_;
     static constexpr int P = H / TS;
     static constexpr int SMEM_CX = 0;   // complex words of shared memory per team (none: shuffles only)
+    static constexpr bool NATURAL = false;   // wavenumber of (register p, lane t) is NOT t + TS p (bit-reversed layout)
     static_assert(TS >= 1 && TS <= 32 && (TS & (TS - 1)) == 0 && TS <= H, "team size: power of two, <= 32, <= H");
     static constexpr int LOGH = ilog2(H);
     static constexpr int LOGTS = ilog2(TS);
@@ -185,6 +186,7 @@ template <typename T, int TWS>
 struct WarpFFT<T, 16, 4, TWS> {
     static constexpr int H = 16, TS = 4, P = 4;
     static constexpr int SMEM_CX = 32;  // two 16-entry slots (fwd2 transforms two sequences at once)
+    static constexpr bool NATURAL = true;    // k = t + 4 p
     int tl, base;
     unsigned tmask;
     Cx<T> wl[3];                        // W16^(tl * r), r = 1..3
@@ -278,6 +280,7 @@ template <typename T, int TWS>
 struct WarpFFT<T, 16, -8, TWS> {
     static constexpr int H = 16, TS = 8, P = 2;
     static constexpr int SMEM_CX = 0;
+    static constexpr bool NATURAL = false;
     int tl, base;
     unsigned tmask;
     bool lo4, b1, b0;                   // tl < 4, bit 1 and bit 0 of tl
@@ -408,6 +411,7 @@ template <typename T, int TWS>
 struct WarpFFT<T, 32, -8, TWS> {
     static constexpr int H = 32, TS = 8, P = 4, ROW = 9;
     static constexpr int SMEM_CX = 4 * ROW;
+    static constexpr bool NATURAL = true;    // k = t + 8 p
     int tl, base, k1, hbit;
     unsigned tmask;
     T sg;
@@ -538,6 +542,27 @@ struct RealFFT {
                           fma(hb, Eb.im, fma(wsb[p].re, Ob.im, wsb[p].im * Ob.re)));
             if (p == 0) { nyqa = (Ea.re - Oa.re) * ha; nyqb = (Eb.re - Ob.re) * hb; }
         }
+    }
+    // UNSCALED split step: X2[p] = E + wk O = 2 fft(x)[k(p)], nyq2 = 2 fft(x)[N/2] -- two FMAs per component instead of
+    // a multiply and two FMAs; the caller folds the 1/2 into a constant it multiplies with anyway.
+    __device__ __forceinline__ void split_raw(const Cx<T> (&z)[P], Cx<T> (&X)[P], T& nyq) const {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const Cx<T> zp = c.mirrored(z, p);
+            const Cx<T> E = cx<T>(z[p].re + zp.re, z[p].im - zp.im);
+            const Cx<T> O = cx<T>(z[p].im + zp.im, zp.re - z[p].re);
+            X[p] = cx<T>(fma(wk[p].re, O.re, fma(-wk[p].im, O.im, E.re)), fma(wk[p].re, O.im, fma(wk[p].im, O.re, E.im)));
+            if (p == 0) nyq = E.re - O.re;
+        }
+    }
+    __device__ __forceinline__ void fwd_raw(Cx<T> (&z)[P], Cx<T> (&X)[P], T& nyq) const {
+        c.fwd(z);
+        split_raw(z, X, nyq);
+    }
+    __device__ __forceinline__ void fwd2_raw(Cx<T> (&za)[P], Cx<T> (&Xa)[P], T& nyqa, Cx<T> (&zb)[P], Cx<T> (&Xb)[P], T& nyqb) const {
+        c.fwd2(za, zb);
+        split_raw(za, Xa, nyqa);
+        split_raw(zb, Xb, nyqb);
     }
     __device__ __forceinline__ void scaled_twiddles(T scale, Cx<T> (&ws)[P]) const {
 #pragma unroll
