@@ -284,24 +284,39 @@ def make_batch_c5(torch, device, seed0, B=8192, **_):
     return env
 
 
-def time_graph(torch, fn_steps, n_steps, reps=3, warm=2):
-    """Capture `fn_steps()` (which enqueues n_steps launches) into a CUDA graph; best-of-`reps` ms per step."""
-    g = torch.cuda.CUDAGraph()
-    fn_steps()
+def time_graph(torch, launches, reps=3, warm=2, chains=1):
+    """Capture the list of callables `launches` (one kernel launch each, on independent batches) into a CUDA graph;
+    best-of-`reps` ms per launch.  chains > 1: consecutive launches alternate between `chains` streams inside the graph
+    (independent batches in flight, as in the headline measurement)."""
+    for fn in launches:
+        fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    streams = [torch.cuda.Stream() for _ in range(chains)] if chains > 1 else []
     with torch.cuda.graph(g):
-        fn_steps()
+        cap = torch.cuda.current_stream()
+        for cs in streams:
+            cs.wait_stream(cap)
+        for i, fn in enumerate(launches):
+            if streams:
+                with torch.cuda.stream(streams[i % chains]):
+                    fn()
+            else:
+                fn()
+        for cs in streams:
+            cap.wait_stream(cs)
     for _ in range(warm):
         g.replay()
     torch.cuda.synchronize()
     best = None
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(100_000)
         e0.record()
         g.replay()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n_steps
+        ms = e0.elapsed_time(e1) / len(launches)
         best = ms if best is None else min(best, ms)
     del g
     return best
@@ -660,19 +675,18 @@ def batch_sweep(torch, device):
     for B, nsub, lanes in ((4096, 10, 4), (4096, 10, 8), (8192, 10, 4), (32768, 10, 4), (32768, 1, 4), (131072, 1, 4)):
         per_batch = B * 1912
         pool = max(2, -(-160_000_000 // per_batch))
+        if B <= 8192:
+            pool = -(-pool // 4) * 4
         envs = [make_batch(torch, device, 7 + i, B=B, team_lanes=lanes, spec=spec, per_env_seeds=False) for i in range(pool)]
         a = torch.from_numpy(np.random.default_rng(B).uniform(0.02, 0.1, (B, M))).to(device)
         reps = max(1, 40 // pool)
-
-        def steps():
-            for _ in range(reps):
-                for e in envs:
-                    e.step_n(a, nsub)
-        ms = time_graph(torch, steps, reps * pool)
+        launches = [(lambda e=e: e.step_n(a, nsub)) for _ in range(reps) for e in envs]
+        chains = 4 if (B <= 8192 and pool % 4 == 0) else 1          # small batches: independent batches in flight, as the headline
+        ms = time_graph(torch, launches, chains=chains)
         alive = all(int((e.status != 0).sum()) == 0 for e in envs)
         gbs = per_batch / (ms * 1e-3) / 1e9
         tf = B * nsub * FLOPS_PER_ENV_STEP / (ms * 1e-3) / 1e12
-        out.append({"envs": B, "n_sub": nsub, "lanes_per_env": lanes, "launch_us": ms * 1e3,
+        out.append({"envs": B, "n_sub": nsub, "lanes_per_env": lanes, "batches_in_flight": chains, "launch_us": ms * 1e3,
                     "env_steps_per_s": B * nsub / (ms * 1e-3), "hbm_frac": gbs / peak, "fp64_frac": tf / fp64_peak,
                     "all_envs_alive": alive})
         del envs
@@ -695,11 +709,8 @@ def other_configs(torch, device, only=None):
         k.setup_basis(m, "hat")
     a = torch.as_tensor(rng.normal(0, 1e-3, (B, m)), device=device)
 
-    def ks_steps():
-        for k in pool:
-            k.step_n(a, 10, want_reward=False)
-    ms = time_graph(torch, ks_steps, len(pool))
-    res["c3_ks_n64_x8192"] = {"launch_us": ms * 1e3, "value": B * 10 / (ms * 1e-3), "unit": "env-steps/s", "n_sub": 10,
+    ms = time_graph(torch, [(lambda k=k: k.step_n(a, 10, want_reward=False)) for k in pool], chains=2)
+    res["c3_ks_n64_x8192"] = {"launch_us": ms * 1e3, "batches_in_flight": 2, "value": B * 10 / (ms * 1e-3), "unit": "env-steps/s", "n_sub": 10,
                               "hbm_frac": B * BYTES_KS / (ms * 1e-3) / 1e9 / peak,
                               "fp64_frac": B * 10 * FLOPS_KS_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
                               "alive": all(int((k.status != 0).sum()) == 0 for k in pool)}
@@ -741,11 +752,8 @@ def other_configs(torch, device, only=None):
     pool = [make_batch_c5(torch, device, 42 + i, B=B) for i in range(10)]
     a5 = torch.as_tensor(rng.uniform(0.0, 0.02, (B, M)), device=device)
 
-    def c5_steps():
-        for e in pool:
-            e.step_n(a5, NSUB)
-    ms = time_graph(torch, c5_steps, len(pool))
-    res["c5_marl_n32_x8192_per_gpu"] = {"launch_us": ms * 1e3, "value": B * NSUB / (ms * 1e-3), "unit": "env-steps/s", "n_sub": NSUB,
+    ms = time_graph(torch, [(lambda e=e: e.step_n(a5, NSUB)) for e in pool], chains=2)
+    res["c5_marl_n32_x8192_per_gpu"] = {"launch_us": ms * 1e3, "batches_in_flight": 2, "value": B * NSUB / (ms * 1e-3), "unit": "env-steps/s", "n_sub": NSUB,
                                         "hbm_frac": B * BYTES_C5 / (ms * 1e-3) / 1e9 / peak,
                                         "fp64_frac": B * NSUB * FLOPS_PER_ENV_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
                                         "alive": all(int((e.status != 0).sum()) == 0 for e in pool)}
