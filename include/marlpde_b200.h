@@ -178,6 +178,13 @@ const char* mpde_rng_last_error(void);
  * degrees kx, ky in 1..3 -- all DEVICE double arrays) at out[q, i, j] = S(xq[q, j], tq[i]) for nq shifted grids of N points
  * and `rows` times: the [nq, rows, N] table mpde_set_truth consumes (dtype MPDE_F64 / MPDE_F32).  FITPACK bispev
  * semantics (arguments clamped to the spline's domain).  Returns 0 / -1. */
+/* Interpolating tensor-product spline of odd degree k (1 = interp2d kind 'linear', 3 = 'cubic') through z[it][ix] = uu_truth on
+ * the grids x [mx], t [mt] (all DEVICE double): FITPACK regrid / fpregr with s = 0, i.e. what interp2d builds in setGroundTruth
+ * (Burger.py:322-323).  Writes the knots tx [mx+k+1], ty [mt+k+1] and the coefficients c [mx*mt] (c[ix*mt + it], FITPACK order)
+ * that mpde_eval_spline_table consumes.  work_dev: >= mt*mx + 7*(mx+mt) doubles.  Coefficients agree with FITPACK's to rounding
+ * (banded LU instead of Givens rotations on the same totally positive collocation matrix). */
+int mpde_fit_spline(const double* x_dev, int32_t mx, const double* t_dev, int32_t mt, const double* z_dev, int32_t k, double* tx_dev,
+                    double* ty_dev, double* c_dev, double* work_dev, void* stream);
 int mpde_eval_spline_table(const double* tx_dev, int32_t ntx, const double* ty_dev, int32_t nty, const double* c_dev, int32_t kx,
                            int32_t ky, const double* xq_dev, int64_t nq, int32_t N, const double* tq_dev, int64_t rows, void* out_dev,
                            int32_t dtype, void* stream);

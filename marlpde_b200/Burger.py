@@ -264,10 +264,8 @@ class Burger(SpectralEnv):
             newx[newx > self.L] -= self.L
             newx[newx < 0] += self.L
             grids.append(newx)
-        if len(uniq) > 8:       # many distinct shifts (noise > 0 at scale): sample the spline on the device
-            tabs = self.f_truth.rows_device(np.stack(grids), self.tt, self.device, self.dtype)
-        else:
-            tabs = np.stack([self.f_truth.rows(g, self.tt) for g in grids])
+        # fit and sample the spline on the device: no host FITPACK call on the reward path
+        tabs = self.f_truth.rows_device(np.stack(grids), self.tt, self.device, self.dtype)
         self.set_truth_table(tabs, env_map=inv.astype(np.int32) if len(uniq) > 1 else None)
         self._truth_shift = key
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "mpde_reset_turbulence": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mpde_forcing_tables": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mpde_rng_last_error": (C.c_char_p, []),
+    "mpde_fit_spline": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mpde_eval_spline_table": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _vp]),
     "mpde_step_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mpde_step_host_packed": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),

@@ -167,7 +167,7 @@ class BurgerEnvBatch:
                 newx = self.sgs.x + sh
                 newx[newx > L] -= L
                 newx[newx < 0] += L
-                tabs.append(self.sgs.f_truth.rows(newx, self.sgs.tt))
+                tabs.append(self.sgs.f_truth.rows_device(newx[None], self.sgs.tt, d0.device, torch.float64)[0].cpu().numpy())
             self._truth = np.stack(tabs)
             self._tmap = inv.astype(np.int32)
             self.sgs.set_truth_table(self._truth, env_map=self._tmap if len(uniq) > 1 else None)

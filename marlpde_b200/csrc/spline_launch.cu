@@ -1,9 +1,9 @@
 // Tensor-product B-spline evaluation on the device: the ground-truth field S(x, t) that
 // setGroundTruth / getMseReward (/root/reference/python/_model/Burger.py:322-327, 578-589) obtain from
 // scipy.interpolate.interp2d, i.e. FITPACK's bispev on the knots / coefficients of the interpolating spline.
-// The spline is still FITTED on the host (SciPy RectBivariateSpline, the library the reference calls); this kernel
-// samples it for every (shifted grid, time row) pair of a batch, which is the part that scales with the number of
-// environments: out[q, i, j] = S(xq[q, j], tq[i]).
+// mpde_eval_spline_table samples the spline for every (shifted grid, time row) pair of a batch -- the part that scales with
+// the number of environments: out[q, i, j] = S(xq[q, j], tq[i]); mpde_fit_spline (round 2) computes knots and coefficients
+// of the interpolating spline on the device as well (FITPACK regrid with s = 0), so setGroundTruth needs no host fit.
 // Restates FITPACK fpbisp (interval search with clamping to [t_k, t_{n-k-1}]) and fpbspl (de Boor recurrence) in fp64.
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -64,6 +64,82 @@ __global__ void spline_table_kernel(const double* __restrict__ tx, int ntx, cons
     out[idx] = (T)sp;
 }
 
+// ---- interpolating spline FIT: what scipy.interpolate.interp2d / RectBivariateSpline(s = 0) compute on the host --
+// FITPACK regrid / fpregr with s = 0: knots t = [x_0 (k+1 times), x_{k/2+1} .. x_{m-2-k/2}, x_{m-1} (k+1 times)] (odd degree k),
+// coefficients = the solution of the collocation system  sum_ab B_a(x_i) c_ab B_b(t_j) = z_ji.  FITPACK solves it by Givens
+// rotations of the banded observation matrix; the matrix is totally positive, so plain banded LU without pivoting is stable and
+// gives the same coefficients to rounding.  Band layout: ab[i * 7 + (j - i + 3)], |j - i| <= 3.
+constexpr int BW = 7;
+
+__global__ void spline_knots_lu_kernel(const double* __restrict__ x, int mx, const double* __restrict__ y, int my, int k,
+                                       double* __restrict__ tx, double* __restrict__ ty, double* __restrict__ abx,
+                                       double* __restrict__ aby) {
+    const double* g = blockIdx.x == 0 ? x : y;
+    const int m = blockIdx.x == 0 ? mx : my;
+    double* t = blockIdx.x == 0 ? tx : ty;
+    double* ab = blockIdx.x == 0 ? abx : aby;
+    const int n = m + k + 1, k3 = k / 2;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v;
+        if (i <= k) v = g[0];
+        else if (i >= m) v = g[m - 1];
+        else v = g[i - k - 1 + k3 + 1];                      // fpregr: tx(kx+2 ..) = x(kx/2+2 ..) (1-based)
+        t[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {     // collocation row i: the k+1 non-zero B-splines at g[i]
+        for (int d = 0; d < BW; ++d) ab[i * BW + d] = 0.0;
+        const double xv = g[i];
+        const int l = find_span(t, n, k, xv);
+        double h[4];
+        bspl(t, k, xv, l, h);
+        for (int a = 0; a <= k; ++a) {
+            const int j = l - k + a;
+            if (j - i + 3 >= 0 && j - i + 3 < BW) ab[i * BW + (j - i + 3)] = h[a];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                 // banded LU, no pivoting (multipliers stored below the diagonal)
+        for (int i = 0; i < m; ++i) {
+            const double piv = ab[i * BW + 3];
+            for (int r = i + 1; r <= i + 3 && r < m; ++r) {
+                const double mlt = ab[r * BW + (i - r + 3)] / piv;
+                ab[r * BW + (i - r + 3)] = mlt;
+                if (mlt != 0.0)
+                    for (int j = i + 1; j <= i + 3 && j < m; ++j) ab[r * BW + (j - r + 3)] -= mlt * ab[i * BW + (j - i + 3)];
+            }
+        }
+    }
+}
+
+// in-place solve of the factored band system for one right-hand side with element stride `st`
+__device__ __forceinline__ void band_solve(const double* __restrict__ ab, int m, double* __restrict__ rhs, int64_t st) {
+    for (int i = 1; i < m; ++i) {
+        double acc = rhs[i * st];
+        for (int j = (i - 3 > 0 ? i - 3 : 0); j < i; ++j) acc -= ab[i * BW + (j - i + 3)] * rhs[j * st];
+        rhs[i * st] = acc;
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double acc = rhs[i * st];
+        for (int j = i + 1; j <= i + 3 && j < m; ++j) acc -= ab[i * BW + (j - i + 3)] * rhs[j * st];
+        rhs[i * st] = acc / ab[i * BW + 3];
+    }
+}
+// along x: one thread per time row; z [my][mx] -> w [my][mx]
+__global__ void spline_solve_x_kernel(const double* __restrict__ abx, int mx, int my, const double* __restrict__ z, double* __restrict__ w) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= my) return;
+    for (int i = 0; i < mx; ++i) w[(int64_t)it * mx + i] = z[(int64_t)it * mx + i];
+    band_solve(abx, mx, w + (int64_t)it * mx, 1);
+}
+// along t: one thread per x coefficient (coalesced across threads); w [my][mx] in place, then c[ix * my + it]
+__global__ void spline_solve_y_kernel(const double* __restrict__ aby, int mx, int my, double* __restrict__ w, double* __restrict__ c) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= mx) return;
+    band_solve(aby, my, w + ix, mx);
+    for (int it = 0; it < my; ++it) c[(int64_t)ix * my + it] = w[(int64_t)it * mx + ix];
+}
+
 thread_local std::string g_serr;
 }  // namespace
 
@@ -85,6 +161,20 @@ int mpde_eval_spline_table(const double* tx_dev, int32_t ntx, const double* ty_d
                                                          static_cast<float*>(out_dev));
     else
         return -1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mpde_fit_spline(const double* x_dev, int32_t mx, const double* t_dev, int32_t mt, const double* z_dev, int32_t k, double* tx_dev,
+                    double* ty_dev, double* c_dev, double* work_dev, void* stream) {
+    if (!x_dev || !t_dev || !z_dev || !tx_dev || !ty_dev || !c_dev || !work_dev) return -1;
+    if ((k != 1 && k != 3) || mx < 2 * (k + 1) || mt < 2 * (k + 1)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* abx = work_dev;
+    double* aby = abx + (size_t)BW * mx;
+    double* w = aby + (size_t)BW * mt;
+    spline_knots_lu_kernel<<<2, 256, 0, st>>>(x_dev, mx, t_dev, mt, k, tx_dev, ty_dev, abx, aby);
+    spline_solve_x_kernel<<<(unsigned)((mt + 63) / 64), 64, 0, st>>>(abx, mx, mt, z_dev, w);
+    spline_solve_y_kernel<<<(unsigned)((mx + 63) / 64), 64, 0, st>>>(aby, mx, mt, w, c_dev);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -141,19 +141,39 @@ class TruthInterpolant:
         out = self._spline()(xs, ts).T
         return out[0] if out.shape[0] == 1 else out
 
+    def fit_device(self, device):
+        """Knots and coefficients of the interpolating spline computed ON THE DEVICE (mpde_fit_spline: FITPACK regrid with
+        s = 0 restated -- same knots, collocation system solved by banded LU), cached per device.  Replaces the host fit
+        (SciPy FITPACK, 0.26 - 0.48 s for a 5001 x 512 DNS) on the MSE-reward path."""
+        import torch
+        from . import _lib as LB
+        if getattr(self, "_tck_dev", None) is not None and self._tck_dev[0] == str(device):
+            return self._tck_dev
+        lib = LB.lib()
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+        x, t, z = up(self.x), up(self.t), up(self.uu)
+        mx, mt, k = x.numel(), t.numel(), self.order
+        assert z.shape == (mt, mx), "truth array must be [len(t), len(x)]"
+        tx = torch.empty(mx + k + 1, dtype=torch.float64, device=device)
+        ty = torch.empty(mt + k + 1, dtype=torch.float64, device=device)
+        c = torch.empty(mx * mt, dtype=torch.float64, device=device)
+        work = torch.empty(mt * mx + 7 * (mx + mt), dtype=torch.float64, device=device)
+        with torch.cuda.device(device):
+            rc = lib.mpde_fit_spline(x.data_ptr(), mx, t.data_ptr(), mt, z.data_ptr(), k, tx.data_ptr(), ty.data_ptr(), c.data_ptr(),
+                                     work.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: mpde_fit_spline failed (degree 1 or 3, at least 2 (k + 1) points per axis)")
+        self._tck_dev = (str(device), tx, ty, c)
+        return self._tck_dev
+
     def rows_device(self, xq, ts, device, dtype):
         """Truth tables on the GPU: xq [nq, N] (one shifted / wrapped grid per row), ts [rows] -> tensor [nq, rows, N].
-        The spline is fitted on the host (FITPACK, as the reference does); its knots and coefficients are uploaded once and
-        sampled by ``mpde_eval_spline_table`` -- the part whose cost grows with the number of distinct shifts."""
+        The spline is fitted on the device (``fit_device``) and sampled by ``mpde_eval_spline_table``."""
         import ctypes as C
         import torch
         from . import _lib as LB
         lib = LB.lib()
-        if getattr(self, "_tck_dev", None) is None or self._tck_dev[0] != str(device):
-            tx, ty, c = self._spline().tck
-            up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
-            self._tck_dev = (str(device), up(tx), up(ty), up(c))
-        _, tx, ty, c = self._tck_dev
+        _, tx, ty, c = self.fit_device(device)
         xq = np.atleast_2d(np.asarray(xq, dtype=np.float64))
         xd = torch.as_tensor(np.ascontiguousarray(xq), device=device)
         td = torch.as_tensor(np.ascontiguousarray(np.asarray(ts, dtype=np.float64)), device=device)

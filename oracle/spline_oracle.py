@@ -66,3 +66,61 @@ def table(tx, ty, c, kx, ky, xq, tq):
             for j, xv in enumerate(xq[q]):
                 out[q, i, j] = bispev(tx, ty, c, kx, ky, xv, tv)
     return out
+
+
+def fit_knots(g, k):
+    """FITPACK fpregr, s = 0, odd degree k: [g_0 (k+1 times), g_{k/2+1} .. g_{m-2-k/2}, g_{m-1} (k+1 times)]."""
+    g = np.asarray(g, dtype=np.float64)
+    m, k3 = len(g), k // 2
+    return np.concatenate((np.full(k + 1, g[0]), g[k3 + 1:m - 1 - k3], np.full(k + 1, g[-1])))
+
+
+def collocation_band(g, t, k):
+    """ab[i, j - i + 3] = B_j(g_i): the interpolation matrix of the knot vector t in band storage (|j - i| <= 3)."""
+    m = len(g)
+    ab = np.zeros((m, 7))
+    for i, xv in enumerate(g):
+        l = find_span(t, k, xv)
+        h = bspl(t, k, xv, l)
+        for a in range(k + 1):
+            j = l - k + a
+            if 0 <= j - i + 3 < 7:
+                ab[i, j - i + 3] = h[a]
+    return ab
+
+
+def band_lu(ab):
+    """In-place LU without pivoting of a band matrix with half-widths 3 (the collocation matrix is totally positive)."""
+    m = len(ab)
+    for i in range(m):
+        piv = ab[i, 3]
+        for r in range(i + 1, min(i + 4, m)):
+            mlt = ab[r, i - r + 3] / piv
+            ab[r, i - r + 3] = mlt
+            for j in range(i + 1, min(i + 4, m)):
+                ab[r, j - r + 3] -= mlt * ab[i, j - i + 3]
+    return ab
+
+
+def band_solve(ab, rhs):
+    """rhs [m, nrhs] -> solution, with the factors of band_lu."""
+    m = len(ab)
+    y = np.array(rhs, dtype=np.float64)
+    for i in range(1, m):
+        for j in range(max(i - 3, 0), i):
+            y[i] -= ab[i, j - i + 3] * y[j]
+    for i in range(m - 1, -1, -1):
+        for j in range(i + 1, min(i + 4, m)):
+            y[i] -= ab[i, j - i + 3] * y[j]
+        y[i] /= ab[i, 3]
+    return y
+
+
+def fit(x, t, z, k):
+    """Interpolating tensor-product spline through z[it, ix] (what interp2d / RectBivariateSpline(s=0) build; FITPACK regrid):
+    returns (tx, ty, c) with c[ix * len(t) + it].  csrc/spline_launch.cu (mpde_fit_spline) follows this function."""
+    tx, ty = fit_knots(x, k), fit_knots(t, k)
+    abx, aby = band_lu(collocation_band(x, tx, k)), band_lu(collocation_band(t, ty, k))
+    w = band_solve(abx, np.asarray(z, dtype=np.float64).T)            # [mx, mt]: along x for every time row
+    c = band_solve(aby, w.T).T                                         # along t for every x coefficient -> [mx, mt]
+    return tx, ty, np.ascontiguousarray(c).reshape(-1)

@@ -172,3 +172,21 @@ def test_masked_reset_keeps_per_env_counters_and_flags_the_host_scalars():
     assert torch.equal(env.v[0], fresh.v) and torch.equal(env.v[3], fresh.v)      # the reset rows restarted exactly
     env.IC(case="turbulence")                                                       # a full reset clears the flag
     env.compute_Ek()
+
+
+@pytest.mark.parametrize("kind,mx,mt", [("cubic", 512, 201), ("cubic", 64, 33), ("linear", 32, 17), ("cubic", 9, 8)])
+def test_spline_fit_on_device_matches_fitpack(kind, mx, mt):
+    """mpde_fit_spline: knots identical to FITPACK's, coefficients of the interpolating spline equal to
+    RectBivariateSpline(s = 0) -- what interp2d builds in setGroundTruth (Burger.py:322-323) -- to rounding."""
+    from scipy.interpolate import RectBivariateSpline
+    from marlpde_b200.hostmath import TruthInterpolant
+    rng = np.random.default_rng(8)
+    x = np.linspace(0, TWO_PI, mx, endpoint=False)
+    t = np.concatenate(([0.], np.cumsum(np.full(mt - 1, 1e-3))))
+    uu = np.sin(x[None, :] + 30 * t[:, None]) + 0.1 * rng.normal(size=(mt, mx))
+    f = TruthInterpolant(x, t, uu, kind=kind)
+    _, tx, ty, c = f.fit_device(torch.device("cuda", 0))
+    k = 3 if kind == "cubic" else 1
+    TX, TY, C = RectBivariateSpline(x, t, uu.T, kx=k, ky=k, s=0).tck
+    assert np.array_equal(tx.cpu().numpy(), TX) and np.array_equal(ty.cpu().numpy(), TY)
+    assert np.max(np.abs(c.cpu().numpy() - C)) <= 1e-12 * np.max(np.abs(C))

@@ -26,3 +26,19 @@ def test_restated_bispev_matches_scipy(kind):
     # on the data points an interpolating spline returns the data
     on = so.table(tx, ty, c, kind, kind, x[None, ::7], t[::5])[0]
     assert np.max(np.abs(on - uu[::5, ::7])) < 1e-12
+
+
+@pytest.mark.parametrize("k,mx,mt", [(3, 32, 21), (1, 16, 9), (3, 9, 8), (3, 64, 101)])
+def test_restated_fit_matches_scipy(k, mx, mt):
+    """oracle.spline_oracle.fit (FITPACK regrid with s = 0: knot placement of fpregr + the collocation solve) against
+    SciPy's RectBivariateSpline -- the stand-in for interp2d(x, t, uu, kind) of setGroundTruth (Burger.py:322-323)."""
+    from scipy.interpolate import RectBivariateSpline
+    from oracle import spline_oracle as so
+    rng = np.random.default_rng(0)
+    x = np.linspace(0, 2 * np.pi, mx, endpoint=False)
+    t = np.arange(mt) * 1e-3
+    z = np.sin(x[None, :] + 3 * t[:, None]) + 0.1 * rng.normal(size=(mt, mx))
+    tx, ty, c = so.fit(x, t, z, k)
+    TX, TY, C = RectBivariateSpline(x, t, z.T, kx=k, ky=k, s=0).tck
+    assert np.array_equal(tx, TX) and np.array_equal(ty, TY)
+    assert np.max(np.abs(c - C)) <= 1e-13 * np.max(np.abs(C))
