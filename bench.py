@@ -567,6 +567,23 @@ def gpu_arm(args):
     sync()
     e2e_s = e2e_local
     clocks = sampler.stop() if sampler else None
+    # PCIe floor of this box (untimed extra): the same pinned buffers and slot streams moving the same bytes per step in
+    # both directions with no kernel in between -- what e2e can at best reach here
+    floor_us = None
+    if world == 1:
+        n_floor = 40 * depth
+        floor_dev = torch.empty(pipe.out_host[0].numel(), dtype=pipe.out_host[0].dtype, device=device)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for i in range(n_floor):
+            k = i % depth
+            pipe.done[k].synchronize()
+            with torch.cuda.stream(pipe.streams[k]):
+                pipe.act_dev[k].copy_(pipe.act_host[k], non_blocking=True)
+                pipe.out_host[k].copy_(floor_dev, non_blocking=True)
+                pipe.done[k].record()
+        torch.cuda.synchronize()
+        floor_us = (time.perf_counter() - t1) / n_floor * 1e6
     for g in gathers:
         g.poll()
 
@@ -610,6 +627,7 @@ def gpu_arm(args):
             "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": Ke, "batches_in_flight": depth, "us_per_step_per_rank": per_rank_e2e,
+                    "us_per_step": e2e_s / Ke * 1e6, "pcie_floor_us_per_step": floor_us,
                     "cores_per_rank": cores_per_rank,
                     "note": "per RL step of a batch: pinned host actions -> H2D -> step_n -> D2H state+reward -> host waits; "
                             "independent batches overlap (HostPipeline)" +

@@ -727,12 +727,14 @@ struct BurgersWarp {
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
             const int RL = nf * seg + tail;
             const int S = A * RL;
-            auto element = [&](int o) {                                      // o-th number of this environment's state row
-                const int a = o / RL, r = o - a * RL;
+            // (a, r) = (agent, position inside the agent's row) of output number o; tracked incrementally -- the divisions of a
+            // direct o -> (a, r) map cost more than the ten solver steps' worth of state arithmetic at A = N
+            const int npa = A == 1 ? N : N / A;
+            auto element = [&](int a, int r) {
                 T val;
                 if (r < nf * seg) {
-                    const int fld = r / seg, w = r - fld * seg;
-                    const int start = A == 1 ? 0 : a * (N / A) - 1;
+                    const int fld = r >= seg ? 1 : 0, w = r - fld * seg;
+                    const int start = A == 1 ? 0 : a * npa - 1;
                     const int j = (start + w + N) & (N - 1);
                     val = f0[fld * N + j];
                 } else {
@@ -740,10 +742,18 @@ struct BurgersWarp {
                 }
                 return live ? val : inf;                                     // Burger.py:633-643
             };
+            auto advance = [&](int& a, int& r, int d) {
+                r += d;
+                while (r >= RL) { r -= RL; ++a; }
+            };
             if (has && (S & 1) == 0) {
                 // rows of even length: two numbers per 16-byte store, the lanes of a team cover contiguous 16 TS bytes
+                int a0 = (2 * tl) / RL, r0 = 2 * tl - a0 * RL;
                 for (int o = 2 * tl; o < S; o += 2 * TS) {
-                    const Cx<T> out = cx<T>(element(o), element(o + 1));
+                    int a1 = a0, r1 = r0;
+                    advance(a1, r1, 1);
+                    const Cx<T> out = cx<T>(element(a0, r0), element(a1, r1));
+                    advance(a0, r0, 2 * TS);
                     if (prm.peer.mc_state) {
                         st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o), out);
                     } else {
@@ -753,8 +763,10 @@ struct BurgersWarp {
                     }
                 }
             } else if (has) {
+                int a0 = tl / RL, r0 = tl - a0 * RL;
                 for (int o = tl; o < S; o += TS) {
-                    const T out = element(o);
+                    const T out = element(a0, r0);
+                    advance(a0, r0, TS);
                     if (prm.peer.mc_state) {
                         st_multicast(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o, out);
                     } else {
@@ -815,7 +827,8 @@ struct BurgersWarp {
             auto agent_reward = [&](int a) {             // agent a owns points [a N/A, (a+1) N/A)
                 T sum = T(0);
                 for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
-                return live ? -(sum / T(W)) / T(nsub > 0 ? nsub : 1) : -inf;
+                const T mean = W == 1 ? sum : sum / T(W);                     // x / 1 == x: skip the division for per-point agents
+                return live ? -mean / T(nsub > 0 ? nsub : 1) : -inf;
             };
             if (has && (A & 1) == 0) {                   // two agents per 16-byte store
                 for (int a = 2 * tl; a < A; a += 2 * TS) {
