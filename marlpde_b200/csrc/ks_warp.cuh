@@ -61,9 +61,10 @@ struct KSWarp {
         auto tb = [&](int t, int p) { return tab[t * TW + kk[p]]; };
         auto tbN = [&](int t) { return tab[t * TW + H]; };
         enum { TE = 0, TE2 = 1, TQ = 2, TF1 = 3, TF2 = 4, TF3 = 5, TG = 6 };
-        Cx<T> ws_nl[P], ws1[P];
-        f.scaled_twiddles(invN * invN, ws_nl);
+        Cx<T> ws1[P];
         f.scaled_twiddles(T(1), ws1);
+        // the nonlinear term uses the UNSCALED split step (X2 = 2 fft(U^2), U = N u): 1/(2 N^2) is folded into g = -k/2
+        const T nl_scale = T(0.5) * invN * invN;
 
         pdl_wait();                  // everything above reads constant tables only
         pdl_launch_dependents();
@@ -137,13 +138,13 @@ struct KSWarp {
             f.inv(w, wNre, z);
 #pragma unroll
             for (int p = 0; p < P; ++p) z[p] = cx<T>(z[p].re * z[p].re, z[p].im * z[p].im);
-            f.fwd(z, X, XN, invN * invN, ws_nl);
+            f.fwd_raw(z, X, XN);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const T g = tb(TG, p);
+                const T g = tb(TG, p) * nl_scale;
                 out[p] = cx<T>(-g * X[p].im, g * X[p].re);     // (i gk) X, gk = -k/2
             }
-            outNim = tbN(TG) * XN;
+            outNim = (tbN(TG) * nl_scale) * XN;
         };
 
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
@@ -201,21 +202,25 @@ struct KSWarp {
                                  (Nc[p].re + F[p].re) * f3p,
                              Ep * v[p].im + (Nv[p].im + F[p].im) * f1p + T(2) * (Na[p].im + Nb[p].im + T(2) * F[p].im) * f2p +
                                  (Nc[p].im + F[p].im) * f3p);
-                bad |= blown(v[p]);
             }
             const T EN = tbN(TE), f1N = tbN(TF1), f2N = tbN(TF2), f3N = tbN(TF3);
             vN = cx<T>(EN * vN.re + FN * f1N + T(2) * (T(2) * FN) * f2N + FN * f3N,
                        EN * vN.im + NvN * f1N + T(2) * (NaN + NbN) * f2N + NcN * f3N);
-            if (f.dc) {
-                v[0].im = tb(TE, 0) * v0im;
-                bad |= blown(vN);
-            }
+            if (f.dc) v[0].im = tb(TE, 0) * v0im;
             iout += 1;
             tnow += dt;
+            // float32 spectrum chain; the complex64 cast is also where the reference detects a blow-up (KS.py:7,273)
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                acc32[p] = __fadd_rn(acc32[p], ek_row_f32((float)v[p].re, (float)v[p].im, N, dxf));
-            accN = __fadd_rn(accN, ek_row_f32((float)vN.re, (float)vN.im, N, dxf));
+            for (int p = 0; p < P; ++p) {
+                const float fre = (float)v[p].re, fim = (float)v[p].im;
+                bad |= !(fabsf(fre) <= FLT_MAX && fabsf(fim) <= FLT_MAX);
+                acc32[p] = __fadd_rn(acc32[p], ek_row_f32(fre, fim, N, dxf));
+            }
+            {
+                const float fre = (float)vN.re, fim = (float)vN.im;
+                if (f.dc) bad |= !(fabsf(fre) <= FLT_MAX && fabsf(fim) <= FLT_MAX);
+                accN = __fadd_rn(accN, ek_row_f32(fre, fim, N, dxf));
+            }
 
             if (prm.hist_rows > 0) {
                 live = live && !BW::team_any(f, bad);
