@@ -39,16 +39,36 @@ __global__ void __launch_bounds__(32) burgers_dns1024_kernel(const SpectralParam
     Dns1024<T, VS>::run(prm, smem_raw);
 }
 template <typename T>
+__global__ void __launch_bounds__(64) burgers_dns1024x2_kernel(const SpectralParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Dns1024x2<T>::run(prm, smem_raw);
+}
+template <typename T>
 static bool dns_warp_eligible(const SpectralParams<T>& p) {
     static const bool on = [] { const char* s = std::getenv("MPDE_DNS_WARP"); return !(s && s[0] == '0'); }();
     return on && p.N == 1024 && !(p.flags & (F_ACTIONS | F_SSM | F_DSM | F_FD | F_NO_ADVANCE)) && p.nsub > 0 && !p.state_out && !p.reward_out;
 }
 template <typename T>
 static int launch_dns1024(const SpectralParams<T>& p, cudaStream_t st) {
-    // MPDE_DNS_VREG=1: spectrum in registers (first version of the kernel) instead of shared memory
+    // MPDE_DNS_WARPS=1: one warp per environment (round-2 first design); MPDE_DNS_VREG=1: that kernel with the spectrum in
+    // registers; default: two warps per environment (Dns1024x2)
     static const bool vreg = [] { const char* s = std::getenv("MPDE_DNS_VREG"); return s && s[0] == '1'; }();
-    if (vreg) burgers_dns1024_kernel<T, false><<<(unsigned)p.B, 32, Dns1024<T, false>::smem_bytes(), st>>>(p);
-    else burgers_dns1024_kernel<T, true><<<(unsigned)p.B, 32, Dns1024<T, true>::smem_bytes(), st>>>(p);
+    static const bool one_warp = [] { const char* s = std::getenv("MPDE_DNS_WARPS"); return s && s[0] == '1'; }();
+    if (vreg) {
+        burgers_dns1024_kernel<T, false><<<(unsigned)p.B, 32, Dns1024<T, false>::smem_bytes(), st>>>(p);
+    } else if (one_warp) {
+        burgers_dns1024_kernel<T, true><<<(unsigned)p.B, 32, Dns1024<T, true>::smem_bytes(), st>>>(p);
+    } else {
+        const size_t smem = Dns1024x2<T>::smem_bytes();
+        static std::map<int, bool> configured;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev]) {
+            if (cudaFuncSetAttribute(burgers_dns1024x2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+            configured[dev] = true;
+        }
+        burgers_dns1024x2_kernel<T><<<(unsigned)p.B, 64, smem, st>>>(p);
+    }
     return 1;
 }
 

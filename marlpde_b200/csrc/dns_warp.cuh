@@ -351,4 +351,293 @@ struct Dns1024 {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two warps per environment (CTA of 64 threads): 512 = 8 x 8 x 8.  Each thread holds 8 complex points (T layout
+// j = 64 r + t, F layout k = 64 r + t); three 8-point transforms in registers, two twiddles from shared-memory tables, two
+// conflict-free transposes through shared memory, no shuffles.  Twice the warps per SM sub-partition of the one-warp kernel
+// (1.7 instead of 0.9) and ~100 registers per thread instead of 255: the one-warp kernel is bound by its own latencies.
+// Same arithmetic per wavenumber as Dns1024 (split step, ABCN update, spectrum chain, history rows).
+template <typename T>
+struct Dns1024x2 {
+    using D1 = Dns1024<T, true>;
+    static constexpr int N = 1024, H = 512, NH = 513, NT = 64;
+    static constexpr int ROW = 65;                       // transpose 1: element (k1, n2) at k1 * 65 + n2
+    // shared memory per CTA in complex words: exchange 8 x 65 | T1 8 x 64 | T2 8 x 8 | (cv, cfo) 514 | Fn_old 514 | v 512 | acc (float)
+    static constexpr int CX_WORDS = 8 * ROW + 512 + 64 + 514 + 514 + 512;
+    static size_t smem_bytes() { return sizeof(Cx<T>) * CX_WORDS + sizeof(float) * 516; }
+
+    // 8-point transform in registers, natural order in and out: n = 4 n1 + n2, k = k1 + 2 k2
+    template <bool INV>
+    __device__ __forceinline__ static void fft8(Cx<T> (&x)[8]) {
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+            const Cx<T> a = x[n2] + x[4 + n2], b = x[n2] - x[4 + n2];
+            x[n2] = a;
+            x[4 + n2] = b;                                                   // slot 4 k1 + n2
+        }
+        x[5] = D1::template tw16<2, INV>(x[5]);                              // W8^(n2 k1): W8 = W16^2
+        x[6] = D1::template tw16<4, INV>(x[6]);
+        x[7] = D1::template tw16<6, INV>(x[7]);
+        D1::template dft4<INV>(x[0], x[1], x[2], x[3]);                      // k1 = 0 -> X[0], X[2], X[4], X[6]
+        D1::template dft4<INV>(x[4], x[5], x[6], x[7]);                      // k1 = 1 -> X[1], X[3], X[5], X[7]
+        const Cx<T> y1 = x[4], y2 = x[1], y3 = x[5], y4 = x[2], y5 = x[6], y6 = x[3];
+        x[1] = y1; x[2] = y2; x[3] = y3; x[4] = y4; x[5] = y5; x[6] = y6;   // out[k1 + 2 k2] = slot[4 k1 + k2]
+    }
+
+    // W16^r (forward), r = 0..7
+    __device__ __forceinline__ static Cx<T> w16(int r) {
+        constexpr double c[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508978178, 0.0,
+                                 -0.38268343236508978178, -0.70710678118654752440, -0.92387953251128673848};
+        constexpr double s[8] = {0.0, 0.38268343236508978178, 0.70710678118654752440, 0.92387953251128673848, 1.0,
+                                 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508978178};
+        return cx<T>(T(c[r]), T(-s[r]));
+    }
+
+    // forward: T layout -> F layout; inverse: F -> T (unnormalised).  All 64 threads of the CTA call it.
+    template <bool INV>
+    __device__ __forceinline__ static void fft512(Cx<T> (&z)[8], Cx<T>* E, const Cx<T> (&w1)[7], const Cx<T> (&w2)[7], int t) {
+        // pass-B thread roles: b + 8 k1 for the first in-register pass over a, k1 + 8 c for the second over b
+        const int bB = t & 7, kB = t >> 3;           // t = b + 8 k1
+        const int kC = t & 7, cC = t >> 3;           // t = k1 + 8 c
+        if constexpr (!INV) {
+            fft8<false>(z);                                                          // over r (n1) -> k1
+#pragma unroll
+            for (int r = 1; r < 8; ++r) z[r] = cmul(z[r], w1[r - 1]);               // W512^(t k1)
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) stcx(E + r * ROW + t, z[r]);                // (k1 = r, n2 = t)
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 8; ++a) z[a] = ldcx(E + kB * ROW + 8 * a + bB);     // thread (b, k1): n2 = 8 a + b
+            fft8<false>(z);                                                          // over a -> c
+#pragma unroll
+            for (int c = 1; c < 8; ++c) z[c] = cmul(z[c], w2[c - 1]);               // W64^(b c)
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) stcx(E + 64 * c + 8 * kB + ((bB + kB) & 7), z[c]);      // (c, k1, b), b swizzled by k1
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 8; ++b) z[b] = ldcx(E + 64 * cC + 8 * kC + ((b + kC) & 7));     // thread (k1, c)
+            fft8<false>(z);                                                          // over b -> d: k = k1 + 8 c + 64 d = t + 64 d
+        } else {
+            fft8<true>(z);                                                           // over d -> b
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 8; ++b) stcx(E + 64 * cC + 8 * kC + ((b + kC) & 7), z[b]);
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[c] = ldcx(E + 64 * c + 8 * kB + ((bB + kB) & 7));
+#pragma unroll
+            for (int c = 1; c < 8; ++c) z[c] = cmulc(z[c], w2[c - 1]);
+            fft8<true>(z);                                                           // over c -> a
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 8; ++a) stcx(E + kB * ROW + 8 * a + bB, z[a]);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) z[r] = ldcx(E + r * ROW + t);
+#pragma unroll
+            for (int r = 1; r < 8; ++r) z[r] = cmulc(z[r], w1[r - 1]);
+            fft8<true>(z);                                                           // over k1 -> r
+        }
+    }
+
+    __device__ static void run(const SpectralParams<T>& prm, unsigned char* smem_raw) {
+        const int t = threadIdx.x;
+        const int64_t e = blockIdx.x;
+        Cx<T>* E = reinterpret_cast<Cx<T>*>(smem_raw);
+        Cx<T>* T1 = E + 8 * ROW;
+        Cx<T>* T2 = T1 + 512;
+        Cx<T>* CC = T2 + 64;
+        Cx<T>* FN = CC + 514;
+        Cx<T>* V = FN + 514;
+        float* acc = reinterpret_cast<float*>(V + 512);
+        const int flags = prm.flags;
+        const T dt = prm.dt, invN = T(1) / T(N);
+        const T nu = prm.nu[e];
+        const float dxf = (float)prm.dx;
+        auto tw1024 = [&](int j) {
+            const Cx<T> w = ldcx(prm.tw + (j & 511));
+            return (j & 512) ? cx<T>(-w.re, -w.im) : w;
+        };
+        // both twiddle sets and the Crank-Nicolson factors live in registers (148 -> ~230 of the 255 a 64-thread CTA may use
+        // with 4 CTAs per SM): the kernel is bound by shared-memory wavefronts + FP64 issue, and these were 30 % of the former
+        Cx<T> w1[7], w2[7], cc[8];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            w1[r - 1] = tw1024((2 * r * t) & 1023);                       // W512^(t r)
+            w2[r - 1] = tw1024((16 * (t & 7) * r) & 1023);                // W64^(b c), b = t & 7 (pass-B role), c = r
+        }
+        const T kw0 = prm.kwave[t], dk = prm.kwave[64];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int k = 64 * r + t;
+            const T kwr = prm.kwave[k];
+            const T C = T(0.5) * (kwr * kwr) * nu * dt;
+            const T rr = T(1) / (T(1) + C);
+            cc[r] = cx<T>((T(1) - C) * rr, T(0.5) * dt * rr);
+            acc[k] = prm.acc[e * NH + k];
+            V[k] = ldcx(prm.v + e * NH + k);
+            FN[k] = ldcx(prm.fn + e * NH + k);
+        }
+        if (t == 0) {
+            const T kwN = prm.kwave[H];
+            const T C = T(0.5) * (kwN * kwN) * nu * dt;
+            const T rr = T(1) / (T(1) + C);
+            CC[H] = cx<T>((T(1) - C) * rr, T(0.5) * dt * rr);
+            acc[H] = prm.acc[e * NH + H];
+            FN[H] = ldcx(prm.fn + e * NH + H);
+            FN[H + 1] = ldcx(prm.v + e * NH + H);
+        }
+        const Cx<T> wbase = tw1024(t);                                                        // W1024^t; W1024^k = wbase W16^r
+        const T hs = T(0.25) * invN * invN;
+        const bool was_live = prm.status[e] == 0;
+        bool live = was_live, bad = false;
+        int iout = prm.iout[e];
+        T tnow = prm.tnow[e];
+        Cx<T> z[8];
+        __syncthreads();
+
+        auto to_real = [&]() {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k = 64 * r + t;
+                const Cx<T> wk = cmul(wbase, w16(r));
+                const Cx<T> vr = ldcx(V + k), vm = ldcx(V + ((512 - k) & 511));
+                const Cx<T> Ee = cx<T>(vr.re + vm.re, vr.im - vm.im);
+                const Cx<T> Dd = cx<T>(vr.re - vm.re, vr.im + vm.im);
+                z[r] = cx<T>(fma(-Dd.im, wk.re, fma(Dd.re, wk.im, Ee.re)), fma(Dd.re, wk.re, fma(Dd.im, wk.im, Ee.im)));
+            }
+            {
+                const T vNre = FN[H + 1].re, v0re = V[0].re;
+                const Cx<T> dc = cx<T>(v0re + vNre, v0re - vNre);
+                z[0] = t == 0 ? dc : z[0];
+            }
+            fft512<true>(z, E, w1, w2, t);
+        };
+        to_real();
+
+        const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
+        const int64_t fc_row = (flags & F_FORCING_PER_ENV) ? e : 0;
+        const bool forcing = (flags & F_FORCING) != 0;
+        for (int it = 0; it < nsub; ++it) {
+            if (it == nsub - 1) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    stcx(reinterpret_cast<Cx<T>*>(prm.uprev + e * N) + 64 * r + t, cx<T>(z[r].re * invN, z[r].im * invN));
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) z[r] = cx<T>(z[r].re * z[r].re, z[r].im * z[r].im);
+            fft512<false>(z, E, w1, w2, t);
+            // Hermitian partners through the exchange buffer (natural order)
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) stcx(E + 64 * r + t, z[r]);
+            __syncthreads();
+            const T XN = (z[0].re - z[0].im) * (T(2) * hs);                    // thread 0: fft(u^2/2)[N/2]
+            float fre[8], fim[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int k = 64 * r + t;
+                const Cx<T> wk = cmul(wbase, w16(r));
+                const Cx<T> zm = ldcx(E + ((512 - k) & 511));
+                const Cx<T> Ee = cx<T>(z[r].re + zm.re, z[r].im - zm.im);
+                const Cx<T> Oo = cx<T>(z[r].im + zm.im, zm.re - z[r].re);
+                const Cx<T> X = cx<T>(hs * (Ee.re + fma(wk.re, Oo.re, -(wk.im * Oo.im))), hs * (Ee.im + fma(wk.re, Oo.im, wk.im * Oo.re)));
+                const T kwr = fma(T(r), dk, kw0);
+                const Cx<T> fnn = cx<T>(-kwr * X.im, kwr * X.re);
+                const Cx<T> c = cc[r];
+                const Cx<T> fo = ldcx(FN + k);
+                const Cx<T> vo = ldcx(V + k);
+                Cx<T> vn = cx<T>(fma(c.im, fma(T(-3), fnn.re, fo.re), c.re * vo.re),
+                                 fma(c.im, fma(T(-3), fnn.im, fo.im), c.re * vo.im));
+                if (r == 0 && forcing) {
+                    const int m = t - 1 < 0 ? 0 : (t - 1 > 2 ? 2 : t - 1);
+                    const Cx<T> F = ldcx(prm.fcoef + (fc_row * prm.stepper + iout % prm.stepper) * 3 + m);
+                    const T wgt = (t >= 1 && t <= 3) ? T(2) * c.im : T(0);
+                    vn = cx<T>(fma(wgt, F.re, vn.re), fma(wgt, F.im, vn.im));
+                }
+                fre[r] = (float)vn.re;
+                fim[r] = (float)vn.im;
+                // V[k] is read by the partner thread too (as v[512 - k] in to_real only, after the barrier below): safe to overwrite
+                stcx(V + k, vn);
+                stcx(FN + k, fnn);
+            }
+            iout += 1;
+            tnow += dt;
+            if (t == 0) {
+                const Cx<T> c = CC[H], vN = FN[H + 1];
+                const T fnnN = prm.kwave[H] * XN;
+                const Cx<T> vn = cx<T>(c.re * vN.re, fma(c.im, fma(T(-3), fnnN, FN[H].im), c.re * vN.im));
+                FN[H + 1] = vn;
+                FN[H] = cx<T>(T(0), fnnN);
+                const float fNre = (float)vn.re, fNim = (float)vn.im;
+                bad |= !(fabsf(fNre) <= FLT_MAX && fabsf(fNim) <= FLT_MAX);
+                acc[H] = __fadd_rn(acc[H], ek_row_f32(fNre, fNim, N, dxf));
+            }
+            const bool write_hist = prm.hist_rows > 0 && iout < prm.hist_rows;
+            const int64_t hrow = e * prm.hist_rows + iout;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                bad |= !(fabsf(fre[r]) <= FLT_MAX && fabsf(fim[r]) <= FLT_MAX);
+                const float a = __fadd_rn(acc[64 * r + t], ek_row_f32(fre[r], fim[r], N, dxf));
+                acc[64 * r + t] = a;
+            }
+            // one barrier: the new v / Fn_old / Nyquist values are visible, and (with history) the blow-up vote
+            if (write_hist) live = live && !__syncthreads_or(bad);
+            else __syncthreads();
+            if (write_hist && live) {
+                const double bdiv = (double)(iout + 1), rdiv = 1.0 / bdiv;
+                auto quot = [&](float a_) {
+                    const double a = (double)a_, q0 = a * rdiv;
+                    return fma(fma(-q0, bdiv, a), rdiv, q0);
+                };
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int k = 64 * r + t;
+                    if (prm.vv_hist) {
+                        Cx<float> c; c.re = fre[r]; c.im = fim[r];
+                        prm.vv_hist[hrow * N + k] = c;
+                        if (k != 0) { c.im = -c.im; prm.vv_hist[hrow * N + N - k] = c; }
+                    }
+                    if (prm.ektt_hist) prm.ektt_hist[hrow * NH + k] = quot(acc[k]);
+                }
+                if (t == 0) {
+                    const Cx<T> vN = FN[H + 1];
+                    if (prm.vv_hist) { Cx<float> c; c.re = (float)vN.re; c.im = (float)vN.im; prm.vv_hist[hrow * N + H] = c; }
+                    if (prm.ektt_hist) prm.ektt_hist[hrow * NH + H] = quot(acc[H]);
+                }
+            }
+            to_real();
+            if (write_hist && live && prm.uu_hist) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    stcx(reinterpret_cast<Cx<T>*>(prm.uu_hist + hrow * N) + 64 * r + t, cx<T>(z[r].re * invN, z[r].im * invN));
+            }
+        }
+        if (nsub > 0) {
+            const bool blew = __syncthreads_or(bad);
+            if (was_live && blew && t == 0) prm.status[e] = 1;
+            live = live && !blew;
+            if (live) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int k = 64 * r + t;
+                    stcx(prm.v + e * NH + k, V[k]);
+                    stcx(prm.fn + e * NH + k, FN[k]);
+                }
+                if (t == 0) {
+                    stcx(prm.v + e * NH + H, FN[H + 1]);
+                    stcx(prm.fn + e * NH + H, FN[H]);
+                    prm.iout[e] = iout;
+                    prm.tnow[e] = tnow;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) prm.acc[e * NH + 64 * r + t] = acc[64 * r + t];
+            if (t == 0) prm.acc[e * NH + H] = acc[H];
+        }
+    }
+};
+
 }  // namespace mpde
