@@ -54,13 +54,19 @@ int launch_warp(const SpectralParams<T>& p, cudaStream_t st) {
 }
 
 // structural-flag specialisations compiled for the hot grid sizes (fp64); LEAN drops the
-// history / MSE / multi-column-forcing branches when the call does not need them
+// history / MSE / multi-column-forcing branches when the call does not need them (burgers_warp.cuh: LEAN)
 template <typename T, int N, int TS, int SF>
 int launch_warp_lean(const SpectralParams<T>& p, cudaStream_t st) {
-    const bool lean = p.hist_rows == 0 && !(p.reward_mode == REWARD_MSE && p.truth) && p.stepper == 1 && p.version != 1;
+    const bool slim = p.hist_rows == 0 && p.stepper == 1 && p.version != 1;
+    const bool mse = p.reward_mode == REWARD_MSE && p.truth;
+    const bool lean = slim && !mse;
     const bool hot = lean && p.nsub > 0 && p.state_out && p.A == 1 && (p.version == 0 || p.version == 2) &&
                      !(p.flags & F_BASIS_DENSE) && p.reward_mode != REWARD_MSE;
     if (hot) return launch_warp<T, N, TS, SF, 2>(p, st);
+    // LEAN = 3: the multi-agent training configuration (MSE reward against a truth table, any agent count) without the
+    // history / multi-column / u_prev branches in the sub-step loop; compiled for the action-driven modes only
+    if constexpr ((SF & F_ACTIONS) != 0)
+        if (slim && mse && p.nsub > 0 && !(p.flags & F_BASIS_DENSE)) return launch_warp<T, N, TS, SF, 3>(p, st);
     return lean ? launch_warp<T, N, TS, SF, 1>(p, st) : launch_warp<T, N, TS, SF, 0>(p, st);
 }
 template <typename T, int N, int TS>

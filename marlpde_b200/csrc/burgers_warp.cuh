@@ -36,9 +36,15 @@ __device__ __forceinline__ float ek_row_f32(float re, float im, int N, float dxf
 // or 2 (per-point rows stored straight from registers), sparse (<= 2-tap) action basis, no MSE reward -- the cold
 // epilogue paths (shared-memory gather with integer divisions, dense basis product, MSE segments) are not even
 // compiled in, which shortens the once-per-launch code the instruction cache has to stream.
+// LEAN = 3 ("multi-agent"): the LEAN = 1 promises except that the MSE reward against a truth table stays (per-agent segment
+// means, any agent count, every state layout), plus "every call advances" and "sparse action basis" as for LEAN = 2: the MARL
+// training configuration.
 template <typename T, int N, int TS_, int SF, int LEAN = 0>
 struct BurgersWarp {
-    static constexpr bool HOT = LEAN >= 2;
+    static constexpr bool HOT = LEAN == 2;
+    static constexpr bool SLIM = LEAN != 0;                   // no history, forcing column period 1, no u_prev tracking
+    static constexpr bool NO_MSE = LEAN == 1 || LEAN == 2;    // LEAN = 3: SLIM, but the MSE reward (and any agent count) stays
+    static constexpr bool TRAIN = LEAN >= 2;                  // every call advances (nsub > 0), sparse (<= 2-tap) action basis
     using R = RealFFT<T, N, TS_>;
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
     // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row
@@ -175,7 +181,7 @@ struct BurgersWarp {
         const int64_t e = first + team;
         const bool has = e < prm.B;
         const int64_t ec = has ? e : 0;
-        const int flags = (SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF)) & (HOT ? ~(F_NO_ADVANCE | F_BASIS_DENSE) : ~0);
+        const int flags = (SF < 0 ? prm.flags : ((prm.flags & ~STRUCT_FLAGS) | SF)) & (TRAIN ? ~(F_NO_ADVANCE | F_BASIS_DENSE) : ~0);
         const bool q1 = !(flags & F_FORCING);
         T* scratch = team_smem + 2 * R::SMEM_CX;
         T* stash = scratch + work_doubles(prm.M);      // per-team constants parked in shared memory (register relief)
@@ -296,7 +302,7 @@ struct BurgersWarp {
         }
 #pragma unroll
         for (int p = 0; p < P; ++p) Uprev[p] = U[p];
-        const bool v1 = !LEAN && prm.version == 1;             // state version 1 needs u of the previous step (dudt)
+        const bool v1 = !SLIM && prm.version == 1;             // state version 1 needs u of the previous step (dudt)
         // Burger_fd keeps u itself in the uprev slot; its previous row lives in the (otherwise unused) Fn_old slot
         const Cx<T>* const uprev_row = fd ? reinterpret_cast<const Cx<T>*>(prm.fn + ec * NH) : reinterpret_cast<const Cx<T>*>(prm.uprev + ec * N);
         if ((flags & F_NO_ADVANCE) && v1 && iout > 0) {
@@ -379,9 +385,9 @@ struct BurgersWarp {
             if (f.dc) stash[4] = kprev_pre;
         }
         __syncwarp(f.c.tmask);
-        const bool hist = !LEAN && prm.hist_rows > 0;
-        const bool do_mse = !LEAN && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
-        const bool multi_col = !LEAN && prm.stepper > 1;
+        const bool hist = !SLIM && prm.hist_rows > 0;
+        const bool do_mse = !NO_MSE && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
+        const bool multi_col = !SLIM && prm.stepper > 1;
         const bool eddy = (flags & F_ACTIONS) && !(flags & F_DFORCE);
         for (int it = 0; it < nsub; ++it) {
           if (fd) {
@@ -538,7 +544,7 @@ struct BurgersWarp {
             // (Burger.py:488) is a complex64 product: float32(dt) * float32(F), rounded to float32.
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                if (!LEAN && it == nsub - 1) Uprev[p] = U[p];       // u before the last sub-step (dudt of state v1)
+                if (!SLIM && it == nsub - 1) Uprev[p] = U[p];       // u before the last sub-step (dudt of state v1)
                 const Cx<T> fnn = cx<T>(-kws[p] * X[p].im, kws[p] * X[p].re);              // i k X
                 const Cx<T> F = q1 ? cx<T>((T)__fmul_rn(dtf, (float)Fh[p].re), (T)__fmul_rn(dtf, (float)Fh[p].im)) : Fh[p];
                 v[p] = cx<T>(fma(cF[p], F.re, fma(cfo[p], fma(T(-3), fnn.re, fn[p].re), cv[p] * v[p].re)),
@@ -651,7 +657,7 @@ struct BurgersWarp {
         if (HOT || (prm.state_out && prm.A == 1 && prm.version <= 2)) {
             // getState, single agent, versions 0/1/2 (Burger.py:617-622): rows are per-point fields, so the
             // lane's two adjacent points go out as one 16-byte store each -- no shared-memory gather
-            const int ver = (LEAN && prm.version == 1) ? 0 : prm.version;
+            const int ver = (SLIM && prm.version == 1) ? 0 : prm.version;
             T left[P], right[P];
             halo(f, U, left, right);
             const T sd2 = inv_dx2 * invN, sdt = invN / dt;
@@ -689,6 +695,7 @@ struct BurgersWarp {
                     st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + c, val);
                 } else {
                     stcx(reinterpret_cast<Cx<T>*>(state_out + off) + c, val);
+#pragma unroll 1
                     for (int q = 0; q < prm.peer.n_data; ++q)
                         stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + c, val);
                 }
@@ -697,7 +704,7 @@ struct BurgersWarp {
         } else if (!HOT && prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store
-            const int ver = (LEAN && prm.version == 1) ? 0 : prm.version, A = prm.A;
+            const int ver = (SLIM && prm.version == 1) ? 0 : prm.version, A = prm.A;
             T left[P], right[P];
             halo(f, U, left, right);
             __syncwarp(f.c.tmask);
@@ -718,8 +725,8 @@ struct BurgersWarp {
                 else if (ver == 4) { a = u; }
                 stcx(reinterpret_cast<Cx<T>*>(f0) + j, a);
                 stcx(reinterpret_cast<Cx<T>*>(f1) + j, b);
-                // Burger.py:653, from the live float64 v
-                ek[kk[p]] = T(0.5) * ((v[p].re * v[p].re + v[p].im * v[p].im) / T(N)) * prm.dx;
+                // Burger.py:653, from the live float64 v (the spectrum tail of state versions 3 / 4)
+                if (ver >= 3) ek[kk[p]] = T(0.5) * ((v[p].re * v[p].re + v[p].im * v[p].im) / T(N)) * prm.dx;
             }
             __syncwarp(f.c.tmask);
             const int nf = (ver == 1 || ver == 2) ? 2 : 1;
@@ -727,50 +734,46 @@ struct BurgersWarp {
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
             const int RL = nf * seg + tail;
             const int S = A * RL;
-            // (a, r) = (agent, position inside the agent's row) of output number o; tracked incrementally -- the divisions of a
-            // direct o -> (a, r) map cost more than the ten solver steps' worth of state arithmetic at A = N
+            // (a, r) = (agent, position inside the agent's row) of output number o = a RL + r, by a multiply-shift division:
+            // exact while o RL < 65536 (here S <= 384 and RL <= 160) -- an integer division per element would cost more
+            // than the ten solver steps' worth of state arithmetic at A = N, and an incremental (a, r) needs divergent loops
+            static_assert(N <= 64, "multiply-shift (a, r) split assumes S * RL < 65536");
             const int npa = A == 1 ? N : N / A;
-            auto element = [&](int a, int r) {
-                T val;
-                if (r < nf * seg) {
-                    const int fld = r >= seg ? 1 : 0, w = r - fld * seg;
-                    const int start = A == 1 ? 0 : a * npa - 1;
-                    const int j = (start + w + N) & (N - 1);
-                    val = f0[fld * N + j];
+            const unsigned magic = 65536u / (unsigned)RL + 1u;
+            const int nfseg = nf * seg, start0 = A == 1 ? N : N - 1;
+            auto element = [&](int o) {
+                const int a = (int)(((unsigned)o * magic) >> 16), r = o - a * RL;
+                int idx;
+                if (r < nfseg) {
+                    const int fld = r >= seg ? 1 : 0;
+                    idx = fld * N + ((start0 + a * npa + r - fld * seg) & (N - 1));
                 } else {
-                    val = f0[2 * N + (r - nf * seg)];
+                    idx = 2 * N + (r - nfseg);
                 }
+                const T val = f0[idx];
                 return live ? val : inf;                                     // Burger.py:633-643
-            };
-            auto advance = [&](int& a, int& r, int d) {
-                r += d;
-                while (r >= RL) { r -= RL; ++a; }
             };
             if (has && (S & 1) == 0) {
                 // rows of even length: two numbers per 16-byte store, the lanes of a team cover contiguous 16 TS bytes
-                int a0 = (2 * tl) / RL, r0 = 2 * tl - a0 * RL;
                 for (int o = 2 * tl; o < S; o += 2 * TS) {
-                    int a1 = a0, r1 = r0;
-                    advance(a1, r1, 1);
-                    const Cx<T> out = cx<T>(element(a0, r0), element(a1, r1));
-                    advance(a0, r0, 2 * TS);
+                    const Cx<T> out = cx<T>(element(o), element(o + 1));
                     if (prm.peer.mc_state) {
                         st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o), out);
                     } else {
                         stcx(reinterpret_cast<Cx<T>*>(state_out + e * S + o), out);
+#pragma unroll 1
                         for (int q = 0; q < prm.peer.n_data; ++q)
                             stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + e * S + o), out);
                     }
                 }
             } else if (has) {
-                int a0 = tl / RL, r0 = tl - a0 * RL;
                 for (int o = tl; o < S; o += TS) {
-                    const T out = element(a0, r0);
-                    advance(a0, r0, TS);
+                    const T out = element(o);
                     if (prm.peer.mc_state) {
                         st_multicast(static_cast<T*>(prm.peer.mc_state) + poff + e * S + o, out);
                     } else {
                         state_out[e * S + o] = out;
+#pragma unroll 1
                         for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.state[q])[poff + e * S + o] = out;
                     }
                 }
@@ -802,15 +805,16 @@ struct BurgersWarp {
                         st_multicast(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a, r);
                     } else {
                         reward_out[e * A + a] = r;
+#pragma unroll 1
                         for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
                     }
                 }
                 if (f.dc && live) prm.kprev[e] = part;
             }
         }
-        if (!HOT && prm.reward_out && prm.reward_mode == REWARD_MSE && prm.truth) {
+        if (!NO_MSE && prm.reward_out && prm.reward_mode == REWARD_MSE && prm.truth) {
             const int A = prm.A, W = N / A;
-            if (nsub == 0) {             // getMseReward() of the current state (Burger.py:578-601)
+            if (!TRAIN && nsub == 0) {   // getMseReward() of the current state (Burger.py:578-601)
                 const int64_t row = iout < prm.truth_rows ? iout : prm.truth_rows - 1;
                 const Cx<T>* tr = reinterpret_cast<const Cx<T>*>(prm.truth + (truth_base + row) * N);
 #pragma unroll
@@ -824,11 +828,23 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) stcx(reinterpret_cast<Cx<T>*>(scratch) + p * TS + tl, mse[p]);
             __syncwarp(f.c.tmask);
+            // x / nsub for every agent of the row: one reciprocal, then the quotient corrected with the exact remainder
+            // (q0 = x r, q = q0 + (x - q0 n) r is the correctly rounded x / n when r is the correctly rounded 1 / n and nothing
+            // under- or overflows); operands outside the safe range take the division itself
+            const T dn = T(nsub > 0 ? nsub : 1), rn = T(1) / dn;
+            auto div_n = [&](T x) {
+                if (nsub <= 1) return x;
+                if (sizeof(T) == 8 && fabs(x) > T(1e-30) && fabs(x) < T(1e30)) {
+                    const T q0 = x * rn;
+                    return fma(fma(-q0, dn, x), rn, q0);
+                }
+                return x / dn;
+            };
             auto agent_reward = [&](int a) {             // agent a owns points [a N/A, (a+1) N/A)
                 T sum = T(0);
                 for (int j = 0; j < W; ++j) sum += scratch[a * W + j];
                 const T mean = W == 1 ? sum : sum / T(W);                     // x / 1 == x: skip the division for per-point agents
-                return live ? -mean / T(nsub > 0 ? nsub : 1) : -inf;
+                return live ? div_n(-mean) : -inf;
             };
             if (has && (A & 1) == 0) {                   // two agents per 16-byte store
                 for (int a = 2 * tl; a < A; a += 2 * TS) {
@@ -837,6 +853,7 @@ struct BurgersWarp {
                         st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a), r);
                     } else {
                         stcx(reinterpret_cast<Cx<T>*>(reward_out + e * A + a), r);
+#pragma unroll 1
                         for (int q = 0; q < prm.peer.n_data; ++q)
                             stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.reward[q]) + poff + e * A + a), r);
                     }
@@ -848,6 +865,7 @@ struct BurgersWarp {
                         st_multicast(static_cast<T*>(prm.peer.mc_reward) + poff + e * A + a, r);
                     } else {
                         reward_out[e * A + a] = r;
+#pragma unroll 1
                         for (int q = 0; q < prm.peer.n_data; ++q) static_cast<T*>(prm.peer.reward[q])[poff + e * A + a] = r;
                     }
                 }

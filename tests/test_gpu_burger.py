@@ -130,10 +130,13 @@ def test_states(golden, ver, A):
 ENV_CASES = ["spec_A1", "spec_A4", "spec_A32_v1", "spec_noise", "mse_A1", "mse_A32", "mse_noise_A4"]
 
 
+@pytest.mark.parametrize("history", [True, False])
 @pytest.mark.parametrize("tag", ENV_CASES)
-def test_environment_episode(golden, tag):
+def test_environment_episode(golden, tag, history):
     """The recorded burger_environment.environment episode (IC hand-off, forcing tables, scripted
-    actions, nIntermediate = 10): states and rewards of every RL step, one launch per RL step."""
+    actions, nIntermediate = 10): states and rewards of every RL step, one launch per RL step.  With history=False the
+    training specialisations of the kernel run (LEAN / HOT for the spectral reward, the multi-agent MSE variant for the
+    truth-table cases) instead of the generic one."""
     from marlpde_b200 import Burger
     from oracle.burger_oracle import truncated_ic
     g = golden("burger_env.npz")
@@ -142,7 +145,7 @@ def test_environment_episode(golden, tag):
     A, ver, stepper, epl = int(A), int(ver), int(stepper), int(epl)
     off = float(g[p + "offset"])
     env = Burger(L=TWO_PI, N=32, dt=1e-3, nu=0.02, tend=0.4, case="zero", forcing=bool(forcing), dforce=bool(dforce),
-                 s=stepper, version=ver, numAgents=A, offset=off, history=True)
+                 s=stepper, version=ver, numAgents=A, offset=off, history=history)
     env.setup_basis(32, "hat")
     env.randfac1, env.randfac2 = g[p + "randfac1"], g[p + "randfac2"]
     if spectral:
@@ -163,8 +166,8 @@ def test_environment_episode(golden, tag):
     assert rel(env.u, g[p + "sgs_u_final"]) < 1e-10
     assert rel(env.v, g[p + "sgs_v_final"]) < 1e-10
     assert env.ioutnum == epl * 10
-    # history rows written by the kernel
-    assert rel(env.uu[env.ioutnum], g[p + "sgs_u_final"]) < 1e-10
+    if history:          # history rows written by the kernel
+        assert rel(env.uu[env.ioutnum], g[p + "sgs_u_final"]) < 1e-10
 
 
 def test_wavenumber_table_is_numpy_fftfreq():
@@ -269,3 +272,29 @@ def test_host_buffer_step_equals_device_step(golden):
         st, rw = pipe.collect(k)
         assert torch.equal(st, st_ref.cpu()) and torch.equal(rw, rw_ref.cpu())
     assert torch.equal(envs[1].v, ref_env.v)
+
+
+@pytest.mark.parametrize("A,ver", [(1, 0), (4, 0), (32, 0), (4, 2), (8, 3), (32, 4)])
+def test_multi_agent_mse_variant_equals_generic_kernel(A, ver):
+    """history=False + MSE truth table selects the multi-agent training specialisation of the step kernel (no history /
+    multi-column forcing / u_prev branches in the sub-step loop); it must reproduce the generic kernel's bits in state,
+    per-agent reward and spectrum for every agent count and state layout."""
+    from marlpde_b200 import Burger
+    B, N = 7, 32
+    rng = np.random.default_rng(100 * A + ver)
+    truth = rng.normal(1.0, 0.3, (41, N))
+    acts = rng.uniform(0.0, 0.02, (3, B, 32))
+    out = []
+    for history in (True, False):
+        env = Burger(L=TWO_PI, N=N, dt=1e-3, nu=0.02, nsteps=40, case="turbulence", forcing=False, dforce=False,
+                     seed=42 + np.arange(B), version=ver, numAgents=A, nenvs=B, history=history)
+        env.setup_basis(32, "hat")
+        env.set_truth_table(truth[None])
+        rows = []
+        for s in range(3):
+            st, rw = env.step_n(acts[s], 10)
+            rows.append((st.clone(), rw.clone()))
+        rows.append((env.v.clone(), env.getMseReward().clone()))        # nsub = 0: reward of the current state
+        out.append(rows)
+    for (a0, b0), (a1, b1) in zip(*out):
+        assert torch.equal(a0, a1) and torch.equal(b0, b1)
