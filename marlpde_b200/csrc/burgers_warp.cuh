@@ -58,14 +58,14 @@ struct BurgersWarp {
         return scr;
     }
 
-    // all cross-lane traffic is scoped to the team (f.c.tmask): teams share a warp but never
-    // each other's control flow or data
+    // all cross-lane traffic is scoped to the team: teams share a warp but never each other's data, and -- unless the
+    // kernel variant promised warp-uniform control flow (R::whole_warp) -- never each other's control flow
     __device__ __forceinline__ static bool team_any(const R& f, bool pred) {
-        return __ballot_sync(f.c.tmask, pred) != 0u;
+        return (__ballot_sync(f.c.smask, pred) & f.c.tmask) != 0u;
     }
     __device__ __forceinline__ static T team_sum(const R& f, T x) {
 #pragma unroll
-        for (int h = TS / 2; h >= 1; h >>= 1) x += shfl_xor(x, h, f.c.tmask);
+        for (int h = TS / 2; h >= 1; h >>= 1) x += shfl_xor(x, h, f.c.smask);
         return x;
     }
     // Real field stored as x[p] = (x_{2j}, x_{2j+1}), j = p*TS + tl.  Returns the left
@@ -82,14 +82,14 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 if constexpr (P == 1) {
-                    right[p] = shfl(x[p].re, lr, f.c.tmask);
-                    left[p] = shfl(x[p].im, ll, f.c.tmask);
+                    right[p] = shfl(x[p].re, lr, f.c.smask);
+                    left[p] = shfl(x[p].im, ll, f.c.smask);
                 } else {
                     // the SENDER picks the register: lane 0 holds the point right of lane TS-1's register p-1 ...
                     const T sr = (tl == 0) ? x[(p + 1) % P].re : x[p].re;          // wanted by my left neighbour
                     const T sl = (tl == TS - 1) ? x[(p + P - 1) % P].im : x[p].im;  // wanted by my right neighbour
-                    right[p] = shfl(sr, lr, f.c.tmask);
-                    left[p] = shfl(sl, ll, f.c.tmask);
+                    right[p] = shfl(sr, lr, f.c.smask);
+                    left[p] = shfl(sl, ll, f.c.smask);
                 }
             }
         }
@@ -177,6 +177,9 @@ struct BurgersWarp {
         T* const team_smem = smem + (size_t)(warp * TPW + team) * scr;
         R f;
         f.init(prm.tw, reinterpret_cast<Cx<T>*>(team_smem));
+        // the training variants have warp-uniform control flow around every collective (mode flags and trip counts are
+        // launch-wide; per-environment conditions only guard loads, stores and selects)
+        if constexpr (TRAIN) f.whole_warp();
         const int tl = f.c.tl;
         const int64_t e = first + team;
         const bool has = e < prm.B;
@@ -321,7 +324,7 @@ struct BurgersWarp {
         if (flags & F_ACTIONS) {
             if (flags & F_BASIS_DENSE) {
                 for (int i = tl; i < prm.M; i += TS) scratch[i] = prm.actions[ec * prm.M + i];
-                __syncwarp(f.c.tmask);
+                __syncwarp(f.c.smask);
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     T val[2];
@@ -334,7 +337,7 @@ struct BurgersWarp {
                     }
                     fa[p] = cx<T>(val[0], val[1]);
                 }
-                __syncwarp(f.c.tmask);
+                __syncwarp(f.c.smask);
             } else {
 #pragma unroll
                 for (int p = 0; p < P; ++p)
@@ -384,7 +387,7 @@ struct BurgersWarp {
             for (int p = 0; p < P; ++p) stash[5 + kk[p]] = ek_pre[p];
             if (f.dc) stash[4] = kprev_pre;
         }
-        __syncwarp(f.c.tmask);
+        __syncwarp(f.c.smask);
         const bool hist = !SLIM && prm.hist_rows > 0;
         const bool do_mse = !NO_MSE && prm.reward_mode == REWARD_MSE && prm.truth != nullptr;
         const bool multi_col = !SLIM && prm.stepper > 1;
@@ -661,53 +664,70 @@ struct BurgersWarp {
             T left[P], right[P];
             halo(f, U, left, right);
             const T sd2 = inv_dx2 * invN, sdt = invN / dt;
-            // Stage this team's row in its scratch area; then the WARP writes whole rows: 16 consecutive lanes cover 256
-            // contiguous bytes of one environment's row.  (A 4-lane team by itself covers 64 bytes per store instruction: fine
-            // for HBM, but in the fused gather those stores travel over NVLink, whose write efficiency follows the size of
-            // the contiguous segment: 8 GPUs reached 0.55 TB/s of ingress with 64-byte segments.)
             const int rl_shift = ilog2(H) + (ver == 0 ? 0 : 1);        // complex words per state row = 1 << rl_shift
-            Cx<T>* const stage = reinterpret_cast<Cx<T>*>(scratch);
             const Cx<T> ii = cx<T>(inf, inf);
+            Cx<T> ra[P], rb[P];                                       // first / second field of the row at this lane's points
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const int j = p * TS + tl;
                 const Cx<T> u = cx<T>(U[p].re * invN, U[p].im * invN);
                 const Cx<T> d2 = cx<T>((left[p] - T(2) * U[p].re + U[p].im) * sd2, (U[p].re - T(2) * U[p].im + right[p]) * sd2);
                 if (ver == 0) {
-                    stcx(stage + j, live ? d2 : ii);
+                    ra[p] = d2;
                 } else if (ver == 1) {
-                    const Cx<T> dudt = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
-                    stcx(stage + j, live ? dudt : ii);
-                    stcx(stage + H + j, live ? d2 : ii);
+                    ra[p] = cx<T>((U[p].re - Uprev[p].re) * sdt, (U[p].im - Uprev[p].im) * sdt);
+                    rb[p] = d2;
                 } else {
-                    stcx(stage + j, live ? u : ii);
-                    stcx(stage + H + j, live ? cx<T>(u.re * u.re, u.im * u.im) : ii);
+                    ra[p] = u;
+                    rb[p] = cx<T>(u.re * u.re, u.im * u.im);
                 }
+                if (!live) ra[p] = rb[p] = ii;
             }
-            __syncwarp();                   // the whole warp: every lane is here (mode flags and trip counts are warp-uniform)
-            for (int idx = lane; idx < (TPW << rl_shift); idx += 32) {
-                const int t = idx >> rl_shift, c = idx & ((1 << rl_shift) - 1);
-                if (first + t >= prm.B) continue;
-                const Cx<T> val = ldcx(reinterpret_cast<const Cx<T>*>(smem + (size_t)(warp * TPW + t) * scr + 2 * R::SMEM_CX) + c);
-                const int64_t off = (first + t) * ((int64_t)2 << rl_shift);         // row start, in T
-                // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
-                if (prm.peer.mc_state) {      // one multicast store reaches every rank's buffer (this one included)
-                    st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + c, val);
-                } else {
-                    stcx(reinterpret_cast<Cx<T>*>(state_out + off) + c, val);
+            if (prm.peer.mc_state == nullptr && prm.peer.n_data == 0) {
+                // one GPU: every lane stores its own points (a team covers 64 contiguous bytes per store instruction)
+                if (has) {
+                    Cx<T>* const row = reinterpret_cast<Cx<T>*>(state_out + e * ((int64_t)2 << rl_shift));
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        stcx(row + p * TS + tl, ra[p]);
+                        if (ver != 0) stcx(row + H + p * TS + tl, rb[p]);
+                    }
+                }
+            } else {
+                // Fused gather: stage this team's row in its scratch area; then the WARP writes whole rows: 16 consecutive
+                // lanes cover 256 contiguous bytes of one environment's row.  (Those stores travel over NVLink, whose write
+                // efficiency follows the size of the contiguous segment: 8 GPUs reached 0.55 TB/s of ingress with the 64-byte
+                // segments a 4-lane team covers by itself, 0.60 - 0.66 TB/s with whole rows.)
+                Cx<T>* const stage = reinterpret_cast<Cx<T>*>(scratch);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    stcx(stage + p * TS + tl, ra[p]);
+                    if (ver != 0) stcx(stage + H + p * TS + tl, rb[p]);
+                }
+                __syncwarp();               // the whole warp: every lane is here (mode flags and trip counts are warp-uniform)
+                for (int idx = lane; idx < (TPW << rl_shift); idx += 32) {
+                    const int t = idx >> rl_shift, c = idx & ((1 << rl_shift) - 1);
+                    if (first + t >= prm.B) continue;
+                    const Cx<T> val = ldcx(reinterpret_cast<const Cx<T>*>(smem + (size_t)(warp * TPW + t) * scr + 2 * R::SMEM_CX) + c);
+                    const int64_t off = (first + t) * ((int64_t)2 << rl_shift);         // row start, in T
+                    // local row + the same row in every peer's gather buffer (multi-GPU, PeerSink)
+                    if (prm.peer.mc_state) {      // one multicast store reaches every rank's buffer (this one included)
+                        st_multicast(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off) + c, val);
+                    } else {
+                        stcx(reinterpret_cast<Cx<T>*>(state_out + off) + c, val);
 #pragma unroll 1
-                    for (int q = 0; q < prm.peer.n_data; ++q)
-                        stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + c, val);
+                        for (int q = 0; q < prm.peer.n_data; ++q)
+                            stcx(reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.state[q]) + poff + off) + c, val);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         } else if (!HOT && prm.state_out) {
             // getState (Burger.py:604-675) through a shared-memory gather so that every
             // version / agent-window layout becomes one coalesced row store
             const int ver = (SLIM && prm.version == 1) ? 0 : prm.version, A = prm.A;
             T left[P], right[P];
             halo(f, U, left, right);
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
             T* f0 = scratch;
             T* f1 = f0 + N;
             T* ek = f1 + N;
@@ -728,21 +748,22 @@ struct BurgersWarp {
                 // Burger.py:653, from the live float64 v (the spectrum tail of state versions 3 / 4)
                 if (ver >= 3) ek[kk[p]] = T(0.5) * ((v[p].re * v[p].re + v[p].im * v[p].im) / T(N)) * prm.dx;
             }
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
             const int nf = (ver == 1 || ver == 2) ? 2 : 1;
             const int seg = A == 1 ? N : N / A + 2;
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
             const int RL = nf * seg + tail;
             const int S = A * RL;
             // (a, r) = (agent, position inside the agent's row) of output number o = a RL + r, by a multiply-shift division:
-            // exact while o RL < 65536 (here S <= 384 and RL <= 160) -- an integer division per element would cost more
-            // than the ten solver steps' worth of state arithmetic at A = N, and an incremental (a, r) needs divergent loops
-            static_assert(N <= 64, "multiply-shift (a, r) split assumes S * RL < 65536");
+            // exact while o RL < 2^22 (here o < S <= 2.5 N and RL <= 2.5 N, N <= 256) -- an integer division per element would
+            // cost more than the ten solver steps' worth of state arithmetic at A = N, and an incremental (a, r) needs
+            // divergent loops
+            static_assert(N <= 256, "multiply-shift (a, r) split assumes S * RL < 2^22 and S * 2^22 / 3 < 2^32");
             const int npa = A == 1 ? N : N / A;
-            const unsigned magic = 65536u / (unsigned)RL + 1u;
+            const unsigned magic = (1u << 22) / (unsigned)RL + 1u;
             const int nfseg = nf * seg, start0 = A == 1 ? N : N - 1;
             auto element = [&](int o) {
-                const int a = (int)(((unsigned)o * magic) >> 16), r = o - a * RL;
+                const int a = (int)(((unsigned)o * magic) >> 22), r = o - a * RL;
                 int idx;
                 if (r < nfseg) {
                     const int fld = r >= seg ? 1 : 0;
@@ -778,7 +799,7 @@ struct BurgersWarp {
                     }
                 }
             }
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
         }
 
         if (spec_reward) {
@@ -794,7 +815,7 @@ struct BurgersWarp {
                     const T q = fabs(er - es) / er;
                     stash[5 + kk[p]] = q * q;
                 }
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
             T part = T(0);
             for (int k = 1; k < H; ++k) part += stash[5 + k];
             part = part / T(H - 1);
@@ -824,10 +845,10 @@ struct BurgersWarp {
                     mse[p] = cx<T>(da * da, db * db);
                 }
             }
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
 #pragma unroll
             for (int p = 0; p < P; ++p) stcx(reinterpret_cast<Cx<T>*>(scratch) + p * TS + tl, mse[p]);
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
             // x / nsub for every agent of the row: one reciprocal, then the quotient corrected with the exact remainder
             // (q0 = x r, q = q0 + (x - q0 n) r is the correctly rounded x / n when r is the correctly rounded 1 / n and nothing
             // under- or overflows); operands outside the safe range take the division itself

@@ -95,7 +95,7 @@ struct KSWarp {
         for (int p = 0; p < P; ++p) { fa[p] = cx<T>(0, 0); F[p] = cx<T>(0, 0); }
         if (flags & F_ACTIONS) {
             for (int i = tl; i < prm.M; i += TS) scratch[i] = prm.actions[ec * prm.M + i];
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 T val[2];
@@ -113,7 +113,7 @@ struct KSWarp {
                 }
                 fa[p] = cx<T>(val[0], val[1]);
             }
-            __syncwarp(f.c.tmask);
+            __syncwarp(f.c.smask);
             if (flags & F_DFORCE) {
                 Cx<T> z[P];
 #pragma unroll

@@ -41,8 +41,9 @@ struct WarpFFT {
 
     int tl;                         // lane within the team
     int base;                       // first lane of the team within the warp
-    unsigned tmask;                 // lanes of this team: every shuffle is team-scoped, so teams never
-                                    // depend on each other's control flow (a team may be idle or dead)
+    unsigned tmask;                 // lanes of this team
+    unsigned smask;                 // mask named by every shuffle / __syncwarp: the team (default: teams never depend on each
+                                    // other's control flow, a team may be idle or dead) or the whole warp (whole_warp())
     Cx<T> wx[LOGTS > 0 ? LOGTS : 1];  // cross-lane twiddles, (1,0) on the lower lane of a pair
     Cx<T> wl[P > 1 ? P - 1 : 1];    // in-register twiddles
     int part[P];                    // lane holding wavenumber -k (mod H) for register pp(p)
@@ -61,6 +62,7 @@ struct WarpFFT {
         tl = lane & (TS - 1);
         base = lane & ~(TS - 1);
         tmask = TS == 32 ? 0xffffffffu : (((1u << TS) - 1u) << base);
+        smask = tmask;
 #pragma unroll
         for (int s = 0; s < LOGTS; ++s) {
             const int h = TS >> (s + 1);
@@ -101,7 +103,7 @@ struct WarpFFT {
             const T sg = (tl & h) ? T(-1) : T(1);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const Cx<T> o = shfl_xor(z[p], h, tmask);
+                const Cx<T> o = shfl_xor(z[p], h, smask);
                 const Cx<T> t = cx<T>(fma(sg, z[p].re, o.re), fma(sg, z[p].im, o.im));
                 z[p] = (h == 1) ? t : cmul(t, wx[s]);          // last stage: twiddle is 1
             }
@@ -131,8 +133,8 @@ struct WarpFFT {
             const T sg = (tl & h) ? T(-1) : T(1);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const Cx<T> oa = shfl_xor(za[p], h, tmask);
-                const Cx<T> ob = shfl_xor(zb[p], h, tmask);
+                const Cx<T> oa = shfl_xor(za[p], h, smask);
+                const Cx<T> ob = shfl_xor(zb[p], h, smask);
                 const Cx<T> ta = cx<T>(fma(sg, za[p].re, oa.re), fma(sg, za[p].im, oa.im));
                 const Cx<T> tb = cx<T>(fma(sg, zb[p].re, ob.re), fma(sg, zb[p].im, ob.im));
                 za[p] = (h == 1) ? ta : cmul(ta, wx[s]);
@@ -150,7 +152,7 @@ struct WarpFFT {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const Cx<T> m = (h == 1) ? z[p] : cmulc(z[p], wx[s]);
-                const Cx<T> o = shfl_xor(m, h, tmask);
+                const Cx<T> o = shfl_xor(m, h, smask);
                 z[p] = cx<T>(fma(sg, m.re, o.re), fma(sg, m.im, o.im));
             }
         }
@@ -171,7 +173,7 @@ struct WarpFFT {
     // value held for wavenumber -k (mod H) by the team, for the k of register p
     __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[P], int p) const {
         if constexpr (TS == 1) return z[pp(p)];
-        else return shfl(z[pp(p)], part[p], tmask);
+        else return shfl(z[pp(p)], part[p], smask);
     }
 };
 
@@ -188,7 +190,7 @@ struct WarpFFT<T, 16, 4, TWS> {
     static constexpr int SMEM_CX = 32;  // two 16-entry slots (fwd2 transforms two sequences at once)
     static constexpr bool NATURAL = true;    // k = t + 4 p
     int tl, base;
-    unsigned tmask;
+    unsigned tmask, smask;
     Cx<T> wl[3];                        // W16^(tl * r), r = 1..3
     Cx<T>* sm;
 
@@ -199,6 +201,7 @@ struct WarpFFT<T, 16, 4, TWS> {
         tl = lane & 3;
         base = lane & ~3;
         tmask = 0xfu << base;
+        smask = tmask;
         sm = team_smem;
 #pragma unroll
         for (int r = 1; r < 4; ++r) {           // the table holds W16^m for m < 8; W16^(m+8) = -W16^m  (tl * r <= 9)
@@ -239,9 +242,9 @@ struct WarpFFT<T, 16, 4, TWS> {
     __device__ __forceinline__ void run(Cx<T> (&z)[4]) const {
         dft4<INV>(z);
         twiddle<INV>(z);
-        __syncwarp(tmask);
+        __syncwarp(smask);
         put(z, 0);
-        __syncwarp(tmask);
+        __syncwarp(smask);
         get(z, 0);
         dft4<INV>(z);
     }
@@ -252,10 +255,10 @@ struct WarpFFT<T, 16, 4, TWS> {
         dft4<false>(zb);
         twiddle<false>(za);
         twiddle<false>(zb);
-        __syncwarp(tmask);
+        __syncwarp(smask);
         put(za, 0);
         put(zb, 1);
-        __syncwarp(tmask);
+        __syncwarp(smask);
         get(za, 0);
         get(zb, 1);
         dft4<false>(za);
@@ -263,7 +266,7 @@ struct WarpFFT<T, 16, 4, TWS> {
     }
     // value held for wavenumber -k (mod 16): k = tl + 4 p -> lane (4 - tl) & 3, register 3 - p (tl > 0) or (4 - p) & 3
     __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[4], int p) const {
-        const Cx<T> far = shfl(z[3 - p], base + ((4 - tl) & 3), tmask);
+        const Cx<T> far = shfl(z[3 - p], base + ((4 - tl) & 3), smask);
         return tl == 0 ? z[(4 - p) & 3] : far;
     }
 };
@@ -282,7 +285,7 @@ struct WarpFFT<T, 16, -8, TWS> {
     static constexpr int SMEM_CX = 0;
     static constexpr bool NATURAL = false;
     int tl, base;
-    unsigned tmask;
+    unsigned tmask, smask;
     bool lo4, b1, b0;                   // tl < 4, bit 1 and bit 0 of tl
     Cx<T> wa, wb;                       // W16^(t' c0), W16^(t' (c0 + 1)): t' = tl & 3, c0 = 2 (tl >> 2)
     int part[2];
@@ -299,6 +302,7 @@ struct WarpFFT<T, 16, -8, TWS> {
         tl = lane & 7;
         base = lane & ~7;
         tmask = 0xffu << base;
+        smask = tmask;
         lo4 = tl < 4;
         b1 = (tl & 2) != 0;
         b0 = (tl & 1) != 0;
@@ -321,7 +325,7 @@ struct WarpFFT<T, 16, -8, TWS> {
         if constexpr (!INV) {
             // pass 1 (points j, j+4, j+8, j+12 of column t'): in-register stage, then lanes t' <-> t' + 4
             const Cx<T> s = z[0] + z[1], d = z[0] - z[1];
-            const Cx<T> os = shfl_xor(s, 4, tmask), od = shfl_xor(d, 4, tmask);
+            const Cx<T> os = shfl_xor(s, 4, smask), od = shfl_xor(d, 4, smask);
             const T sg = lo4 ? T(1) : T(-1);
             z[0] = pm(sg, s, os);                                       // y0 = a0 + a2 | y2 = a0 - a2
             z[1] = rot(sg, lo4 ? d : od, lo4 ? od : d);                 // y1 = a1 - i a3 | y3 = a1 + i a3
@@ -330,12 +334,12 @@ struct WarpFFT<T, 16, -8, TWS> {
             const T sg0 = b0 ? T(-1) : T(1), sg1 = b1 ? T(-1) : T(1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const Cx<T> o = shfl_xor(z[q], 1, tmask);
+                const Cx<T> o = shfl_xor(z[q], 1, smask);
                 z[q] = pm(sg0, z[q], o);                                 // a0, a1 (d = 0, 2) | a2, a3 (d = 1, 3)
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const Cx<T> o = shfl_xor(z[q], 2, tmask);
+                const Cx<T> o = shfl_xor(z[q], 2, smask);
                 const Cx<T> plain = pm(sg1, z[q], o);                    // B0 = a0 + a2 | B2 = a0 - a2
                 const Cx<T> turned = rot(-sg1, b1 ? o : z[q], b1 ? z[q] : o);   // B1 = a1 + i a3 | B3 = a1 - i a3
                 z[q] = b0 ? turned : plain;
@@ -355,12 +359,12 @@ struct WarpFFT<T, 16, -8, TWS> {
             const T sg1 = b1 ? T(-1) : T(1), sg0 = b0 ? T(-1) : T(1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const Cx<T> o = shfl_xor(z[q], 2, tmask);
+                const Cx<T> o = shfl_xor(z[q], 2, smask);
                 z[q] = pm(sg1, z[q], o);                                 // a0, a2 | a1, a3
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const Cx<T> o = shfl_xor(z[q], 1, tmask);
+                const Cx<T> o = shfl_xor(z[q], 1, smask);
                 const Cx<T> plain = pm(sg0, z[q], o);                    // y0 = a0 + a2 | y2 = a0 - a2
                 const Cx<T> turned = rot(sg0, b0 ? o : z[q], b0 ? z[q] : o);    // y1 = a1 - i a3 | y3 = a1 + i a3
                 z[q] = b1 ? turned : plain;
@@ -370,7 +374,7 @@ struct WarpFFT<T, 16, -8, TWS> {
             const T sg = lo4 ? T(1) : T(-1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const Cx<T> o = shfl_xor(z[q], 4, tmask);
+                const Cx<T> o = shfl_xor(z[q], 4, smask);
                 z[q] = pm(sg, z[q], o);                                  // a0, a2 | a1, a3
             }
             // lo: x[p=0] = a0 + a2, x[p=2] = a0 - a2;  hi: x[p=1] = a1 + i a3, x[p=3] = a1 - i a3
@@ -398,7 +402,7 @@ struct WarpFFT<T, 16, -8, TWS> {
         twiddle<true>(z);
         second_pass<true>(z);
     }
-    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[2], int q) const { return shfl(z[q], part[q], tmask); }
+    __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[2], int q) const { return shfl(z[q], part[q], smask); }
 };
 
 // 32 points on 8 lanes x 4 registers as 4 x (2 x 4): a 4-point transform in registers, the twiddle W32^(lane r), ONE
@@ -413,7 +417,7 @@ struct WarpFFT<T, 32, -8, TWS> {
     static constexpr int SMEM_CX = 4 * ROW;
     static constexpr bool NATURAL = true;    // k = t + 8 p
     int tl, base, k1, hbit;
-    unsigned tmask;
+    unsigned tmask, smask;
     T sg;
     Cx<T> w1[3];                        // W32^(tl r), r = 1..3
     Cx<T> w2[3];                        // W8^(m h),  m = 1..3 (1 on the lanes with h = 0)
@@ -432,6 +436,7 @@ struct WarpFFT<T, 32, -8, TWS> {
         tl = lane & 7;
         base = lane & ~7;
         tmask = 0xffu << base;
+        smask = tmask;
         k1 = tl & 3;
         hbit = tl >> 2;
         sg = hbit ? T(-1) : T(1);
@@ -447,15 +452,15 @@ struct WarpFFT<T, 32, -8, TWS> {
         Q::template dft4<false>(z);                              // over p -> k1 in registers
 #pragma unroll
         for (int r = 1; r < 4; ++r) z[r] = cmul(z[r], w1[r - 1]);
-        __syncwarp(tmask);
+        __syncwarp(smask);
 #pragma unroll
         for (int r = 0; r < 4; ++r) stcx(sm + r * ROW + tl, z[r]);
-        __syncwarp(tmask);
+        __syncwarp(smask);
 #pragma unroll
         for (int m = 0; m < 4; ++m) z[m] = ldcx(sm + k1 * ROW + 4 * hbit + m);      // lane (k1, h): points n2 = 4 h + m
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const Cx<T> o = shfl_xor(z[m], 4, tmask);
+            const Cx<T> o = shfl_xor(z[m], 4, smask);
             z[m] = cx<T>(fma(sg, z[m].re, o.re), fma(sg, z[m].im, o.im));
         }
 #pragma unroll
@@ -468,13 +473,13 @@ struct WarpFFT<T, 32, -8, TWS> {
         for (int m = 1; m < 4; ++m) z[m] = cmulc(z[m], w2[m - 1]);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const Cx<T> o = shfl_xor(z[m], 4, tmask);
+            const Cx<T> o = shfl_xor(z[m], 4, smask);
             z[m] = cx<T>(fma(sg, z[m].re, o.re), fma(sg, z[m].im, o.im));
         }
-        __syncwarp(tmask);
+        __syncwarp(smask);
 #pragma unroll
         for (int m = 0; m < 4; ++m) stcx(sm + k1 * ROW + 4 * hbit + m, z[m]);
-        __syncwarp(tmask);
+        __syncwarp(smask);
 #pragma unroll
         for (int r = 0; r < 4; ++r) z[r] = ldcx(sm + r * ROW + tl);
 #pragma unroll
@@ -484,7 +489,7 @@ struct WarpFFT<T, 32, -8, TWS> {
     __device__ __forceinline__ void fwd2(Cx<T> (&za)[4], Cx<T> (&zb)[4]) const { fwd(za); fwd(zb); }
     // value held for wavenumber -k (mod 32): k = tl + 8 q -> lane (8 - tl) & 7, register 3 - q (tl > 0) or (4 - q) & 3
     __device__ __forceinline__ Cx<T> mirrored(const Cx<T> (&z)[4], int q) const {
-        const Cx<T> far = shfl(z[3 - q], base + ((8 - tl) & 7), tmask);
+        const Cx<T> far = shfl(z[3 - q], base + ((8 - tl) & 7), smask);
         return tl == 0 ? z[(4 - q) & 3] : far;
     }
 };
@@ -509,6 +514,10 @@ struct RealFFT {
     }
     // wavenumber index 0..H-1 of register p
     __device__ __forceinline__ int k(int p) const { return C::kidx(p, c.tl); }
+    // Promise that all 32 lanes of the warp execute every shuffle / __syncwarp of this object together (warp-uniform control
+    // flow): the collectives then name the compile-time full mask, and the compiler drops the run-time mask validation
+    // (MATCH.ANY + a divergence branch ahead of each group of collectives -- 4 % of the hot kernel's time).
+    __device__ __forceinline__ void whole_warp() { c.smask = 0xffffffffu; }
 
     // z[p] = (x_{2j}, x_{2j+1}), j = p*TS + tl   ->   X[p] = scale * fft(x)[k(p)],
     // nyq = scale * fft(x)[N/2] (real; meaningful on the dc lane only).  z is clobbered.
