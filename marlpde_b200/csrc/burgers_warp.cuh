@@ -47,8 +47,9 @@ struct BurgersWarp {
     static constexpr bool TRAIN = LEAN >= 2;                  // every call advances (nsub > 0), sparse (<= 2-tap) action basis
     using R = RealFFT<T, N, TS_>;
     static constexpr int H = N / 2, TS = R::TS, P = R::P, NH = N / 2 + 1, TPW = 32 / TS;
-    // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row
-    static constexpr int STASH = 6 + H;
+    // shared-memory stash per team: [0..3] Nyquist-mode constants, [4] kPrevRelErr, [5..] reference spectrum row, [RCP..] its
+    // reciprocals (the reward's divisions become correction steps: div_by_rcp)
+    static constexpr int STASH = 6 + 2 * H, RCP = 6 + H;          // [RCP + k]: reciprocal of the reference spectrum row
     // doubles of shared memory per team: [FFT exchange area | work (dense actions / state gather / MSE) | stash]
     __host__ __device__ static constexpr int work_doubles(int M) { return M > 2 * N + N / 2 ? M : 2 * N + N / 2; }
     __host__ __device__ static constexpr int scratch_doubles(int M) {
@@ -248,6 +249,8 @@ struct BurgersWarp {
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
         const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
         T ek_pre[P], kprev_pre = T(0);
+        // the reward's running-mean divisor (iout + 1 at the END of this call) and its reciprocal
+        const double cnt_end = (double)(iout + nsub + 1), rcnt_end = 1.0 / cnt_end;
         if (spec_reward) {
             const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
             const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
@@ -384,7 +387,10 @@ struct BurgersWarp {
         // =============================== sub-steps ==============================================
         if (spec_reward) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) stash[5 + kk[p]] = ek_pre[p];
+            for (int p = 0; p < P; ++p) {
+                stash[5 + kk[p]] = ek_pre[p];
+                stash[RCP + kk[p]] = T(1) / ek_pre[p];
+            }
             if (f.dc) stash[4] = kprev_pre;
         }
         __syncwarp(f.c.smask);
@@ -810,15 +816,15 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p)
                 if (kk[p] >= 1) {
-                    const T es = (T)((double)acc32[p] / (double)(iout + 1));
+                    const T es = (T)div_by_rcp((double)acc32[p], cnt_end, rcnt_end);
                     const T er = stash[5 + kk[p]];
-                    const T q = fabs(er - es) / er;
+                    const T q = div_by_rcp(fabs(er - es), er, stash[RCP + kk[p]]);
                     stash[5 + kk[p]] = q * q;
                 }
             __syncwarp(f.c.smask);
             T part = T(0);
             for (int k = 1; k < H; ++k) part += stash[5 + k];
-            part = part / T(H - 1);
+            part = div_by_rcp(part, T(H - 1), T(1) / T(H - 1));
             const T r = live ? stash[4] - part : -inf;
             if (has) {
                 for (int a = tl; a < A; a += TS) {

@@ -58,6 +58,19 @@ template <typename T> __device__ __forceinline__ bool blown(Cx<T> v) {
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
 // become resident while its predecessor in the stream is still running; it must not touch memory the predecessor
 // writes before pdl_wait() returns (= predecessor complete and flushed).  Without the attribute both are no-ops.
+// a / b through y = 1 / b (the correctly rounded reciprocal, computed earlier and off the critical path): q0 = a y,
+// q = q0 + (a - q0 b) y is the correctly rounded quotient -- the bits of a / b -- as long as nothing under- or overflows
+// (Markstein's correction step); operands outside the safe range take the division itself.  float: division is cheap.
+__device__ __forceinline__ double div_by_rcp(double a, double b, double y) {
+    const double aa = fabs(a), bb = fabs(b);
+    if ((aa == 0.0 || (aa > 1e-250 && aa < 1e250)) && bb > 1e-250 && bb < 1e250) {
+        const double q0 = a * y;
+        return fma(fma(-q0, b, a), y, q0);
+    }
+    return a / b;
+}
+__device__ __forceinline__ float div_by_rcp(float a, float b, float) { return a / b; }
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

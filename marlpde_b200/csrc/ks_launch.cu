@@ -6,15 +6,15 @@ namespace mpde {
 
 // MINB = CTAs (of 64 threads) per SM the register allocation must allow: a batch of thousands of environments runs in
 // several waves, so more resident warps (fewer waves) beats more registers per thread
-template <typename T, int N, int TS, int MINB = 1>
+template <typename T, int N, int TS, int MINB = 1, bool WW = false>
 __global__ void __launch_bounds__(64, MINB) ks_warp_kernel(const SpectralParams<T> prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    KSWarp<T, N, TS>::run(prm, reinterpret_cast<T*>(smem_raw));
+    KSWarp<T, N, TS, WW>::run(prm, reinterpret_cast<T*>(smem_raw));
 }
 
-template <typename T, int N, int TS, int MINB = 1>
+template <typename T, int N, int TS, int MINB = 1, bool WW = false>
 static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
-    using K = KSWarp<T, N, TS>;
+    using K = KSWarp<T, N, TS, WW>;
     constexpr int TPW = K::TPW;
     const int64_t warps = (p.B + TPW - 1) / TPW;
     const int scr = 2 * K::R::SMEM_CX + (p.M > 2 * N + N / 2 ? p.M : 2 * N + N / 2);
@@ -31,7 +31,7 @@ static int launch_ks_warp(const SpectralParams<T>& p, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, ks_warp_kernel<T, N, TS, MINB>, p);
+    cudaLaunchKernelEx(&cfg, ks_warp_kernel<T, N, TS, MINB, WW>, p);
     return 1;
 }
 
@@ -57,6 +57,7 @@ int launch_ks(const SpectralParams<T>& p, cudaStream_t st) {
                 if (const char* s = std::getenv("MPDE_KS_MINB")) minb = std::atoi(s);
                 if (minb == 6) return launch_ks_warp<T, 64, -8, 6>(p, st);
                 if (minb == 5) return launch_ks_warp<T, 64, -8, 5>(p, st);
+                if (p.hist_rows == 0) return launch_ks_warp<T, 64, -8, 4, true>(p, st);     // training: whole-warp collectives
                 return launch_ks_warp<T, 64, -8, 4>(p, st);
             }
             case 32: return launch_ks_warp<T, 64, 32>(p, st);

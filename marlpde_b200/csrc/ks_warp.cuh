@@ -14,7 +14,10 @@ namespace mpde {
 
 constexpr int F_KS_UUROW = 1 << 8;   // the float32 row uu[ioutnum] is current (fou2real was called)
 
-template <typename T, int N, int TS_>
+// WW ("whole warp"): compile-time promise that no history is recorded -- the only place where a team's control flow around
+// a collective depends on its own environment (a blown-up environment stops writing rows) -- so every shuffle and
+// __syncwarp may name the full warp mask (RealFFT::whole_warp).
+template <typename T, int N, int TS_, bool WW = false>
 struct KSWarp {
     using R = RealFFT<T, N, TS_>;
     using BW = BurgersWarp<T, N, TS_, -1, false>;
@@ -46,6 +49,7 @@ struct KSWarp {
         T* const team_smem = smem + (size_t)(warp * TPW + team) * scr_team;
         R f;
         f.init(prm.tw, reinterpret_cast<Cx<T>*>(team_smem));
+        if constexpr (WW) f.whole_warp();
         const int tl = f.c.tl;
         const int64_t e = first + team;
         const bool has = e < prm.B;
@@ -222,7 +226,7 @@ struct KSWarp {
                 accN = __fadd_rn(accN, ek_row_f32(fre, fim, N, dxf));
             }
 
-            if (prm.hist_rows > 0) {
+            if (!WW && prm.hist_rows > 0) {
                 live = live && !BW::team_any(f, bad);
                 if (live && iout < prm.hist_rows) {
                     const int64_t hrow = e * prm.hist_rows + iout;
