@@ -248,14 +248,17 @@ struct BurgersWarp {
         // loads go out as early as possible; the values are parked in shared memory at the end of the prologue
         const int nsub = (flags & F_NO_ADVANCE) ? 0 : prm.nsub;
         const bool spec_reward = prm.reward_out && prm.reward_mode == REWARD_SPECTRAL && nsub > 0;
-        T ek_pre[P], kprev_pre = T(0);
+        T ek_pre[P], rk_pre[P], kprev_pre = T(0);
         // the reward's running-mean divisor (iout + 1 at the END of this call) and its reciprocal
         const double cnt_end = (double)(iout + nsub + 1), rcnt_end = 1.0 / cnt_end;
         if (spec_reward) {
             const int64_t ref = prm.ek_map ? prm.ek_map[ec] : 0;
             const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
 #pragma unroll
-            for (int p = 0; p < P; ++p) ek_pre[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+            for (int p = 0; p < P; ++p) {
+                ek_pre[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
+                rk_pre[p] = prm.ek_rcp[(ref * prm.ek_rows + row) * H + kk[p]];
+            }
             kprev_pre = prm.kprev[ec];
         }
 
@@ -389,7 +392,7 @@ struct BurgersWarp {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 stash[5 + kk[p]] = ek_pre[p];
-                stash[RCP + kk[p]] = T(1) / ek_pre[p];
+                stash[RCP + kk[p]] = rk_pre[p];
             }
             if (f.dc) stash[4] = kprev_pre;
         }
@@ -813,14 +816,32 @@ struct BurgersWarp {
             const int A = prm.A;
             // squared relative errors go back into the stash (over the reference row) and are summed in WAVENUMBER order
             // by every lane: the same sequence of additions whatever the team size (variants must agree bitwise)
+            // every division here is a correction step on a reciprocal computed in the prologue (rcnt_end) or when the
+            // reference was set (stash[RCP + k]); one range check for the whole lane, the divisions themselves otherwise
+            T qq[P];
+            bool safe = true;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double a = (double)acc32[p];
+                const T es = (T)div_rcp_fast(a, cnt_end, rcnt_end);
+                const T er = stash[5 + kk[p]];
+                const T x = fabs(er - es);
+                if (kk[p] >= 1) safe = safe && rcp_ok(a, cnt_end) && rcp_ok(x, er);      // k = 0 is not part of the reward
+                const T q = div_rcp_fast(x, er, stash[RCP + kk[p]]);
+                qq[p] = q * q;
+            }
+            if (!safe) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const T es = (T)((double)acc32[p] / cnt_end);
+                    const T er = stash[5 + kk[p]];
+                    const T q = fabs(er - es) / er;
+                    qq[p] = q * q;
+                }
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p)
-                if (kk[p] >= 1) {
-                    const T es = (T)div_by_rcp((double)acc32[p], cnt_end, rcnt_end);
-                    const T er = stash[5 + kk[p]];
-                    const T q = div_by_rcp(fabs(er - es), er, stash[RCP + kk[p]]);
-                    stash[5 + kk[p]] = q * q;
-                }
+                if (kk[p] >= 1) stash[5 + kk[p]] = qq[p];
             __syncwarp(f.c.smask);
             T part = T(0);
             for (int k = 1; k < H; ++k) part += stash[5 + k];

@@ -1,6 +1,7 @@
 // C ABI of marlpde_b200 (see include/marlpde_b200.h).  Host-side handle management and
 // kernel dispatch; no torch, no CPU compute path: every solver call launches sm_100a kernels.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -82,6 +83,8 @@ template <typename T>
 struct Env : mpde_env {
     SpectralParams<T> prm{};
     std::vector<void*> owned;
+    T* ek_rcp_buf = nullptr;        // reciprocals of the spectrum reference (set_spectrum_ref)
+    int64_t ek_rcp_cap = 0;
     int n_forcing = 0;
 
     template <typename U>
@@ -264,8 +267,28 @@ struct Env : mpde_env {
     }
 
     int set_spectrum_ref(const double* ek, int64_t nref, int64_t rows, const int32_t* map) override {
-        (void)nref;
+        // reciprocals of the table for the step kernels' reward (library-owned; set-up path: drain the device on both sides,
+        // the caller's table may have been produced on any stream and step kernels may be in flight on others)
+        const int64_t n = (ek && nref > 0 && rows > 0) ? nref * rows * (cfg.N / 2) : 0;
+        if (n > ek_rcp_cap) {
+            T* buf = nullptr;
+            CU(cudaDeviceSynchronize());
+            CU(cudaMalloc(&buf, (size_t)n * sizeof(T)));
+            if (ek_rcp_buf) {
+                owned.erase(std::remove(owned.begin(), owned.end(), static_cast<void*>(ek_rcp_buf)), owned.end());
+                cudaFree(ek_rcp_buf);
+            }
+            owned.push_back(buf);
+            ek_rcp_buf = buf;
+            ek_rcp_cap = n;
+        }
+        if (n > 0) {
+            CU(cudaDeviceSynchronize());
+            launches += launch_rcp_table<T>(ek, ek_rcp_buf, n, nullptr);
+            CU(cudaDeviceSynchronize());
+        }
         prm.ek_ref = ek;
+        prm.ek_rcp = n > 0 ? ek_rcp_buf : nullptr;
         prm.ek_rows = rows;
         prm.ek_map = map;
         return 0;

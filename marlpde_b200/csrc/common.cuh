@@ -60,16 +60,19 @@ template <typename T> __device__ __forceinline__ bool blown(Cx<T> v) {
 // writes before pdl_wait() returns (= predecessor complete and flushed).  Without the attribute both are no-ops.
 // a / b through y = 1 / b (the correctly rounded reciprocal, computed earlier and off the critical path): q0 = a y,
 // q = q0 + (a - q0 b) y is the correctly rounded quotient -- the bits of a / b -- as long as nothing under- or overflows
-// (Markstein's correction step); operands outside the safe range take the division itself.  float: division is cheap.
-__device__ __forceinline__ double div_by_rcp(double a, double b, double y) {
+// (Markstein's correction step).  rcp_ok() is that safe range; callers fall back to the division itself outside it (also
+// for non-finite operands, which fail every comparison).  float kernels keep the division: it is cheap.
+__device__ __forceinline__ bool rcp_ok(double a, double b) {
     const double aa = fabs(a), bb = fabs(b);
-    if ((aa == 0.0 || (aa > 1e-250 && aa < 1e250)) && bb > 1e-250 && bb < 1e250) {
-        const double q0 = a * y;
-        return fma(fma(-q0, b, a), y, q0);
-    }
-    return a / b;
+    return (aa == 0.0 || (aa > 1e-250 && aa < 1e250)) && bb > 1e-250 && bb < 1e250;
 }
-__device__ __forceinline__ float div_by_rcp(float a, float b, float) { return a / b; }
+__device__ __forceinline__ bool rcp_ok(float, float) { return false; }
+__device__ __forceinline__ double div_rcp_fast(double a, double b, double y) {
+    const double q0 = a * y;
+    return fma(fma(-q0, b, a), y, q0);
+}
+__device__ __forceinline__ float div_rcp_fast(float a, float b, float) { return a / b; }
+template <typename T> __device__ __forceinline__ T div_by_rcp(T a, T b, T y) { return rcp_ok(a, b) ? div_rcp_fast(a, b, y) : a / b; }
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
