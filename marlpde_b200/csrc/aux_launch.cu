@@ -31,19 +31,20 @@ int launch_spectral_aux(const SpectralParams<T>& p, int equation, int mode, cons
     }
 }
 
-// out[i] = T(1) / T(in[i]): reciprocals of the reward's reference spectrum (set-up, once per mpde_set_spectrum_ref)
+// out[i] = (T(in[i]), T(1) / T(in[i])): the reward's reference spectrum with its reciprocals (set-up, once per
+// mpde_set_spectrum_ref)
 template <typename T>
-__global__ void rcp_table_kernel(const double* __restrict__ in, T* __restrict__ out, int64_t n) {
+__global__ void rcp_table_kernel(const double* __restrict__ in, Cx<T>* __restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = T(1) / (T)in[i];
+    if (i < n) stcx(out + i, cx<T>((T)in[i], T(1) / (T)in[i]));
 }
 template <typename T>
-int launch_rcp_table(const double* in, T* out, int64_t n, cudaStream_t st) {
+int launch_rcp_table(const double* in, Cx<T>* out, int64_t n, cudaStream_t st) {
     if (n > 0) rcp_table_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
     return 1;
 }
-template int launch_rcp_table<double>(const double*, double*, int64_t, cudaStream_t);
-template int launch_rcp_table<float>(const double*, float*, int64_t, cudaStream_t);
+template int launch_rcp_table<double>(const double*, Cx<double>*, int64_t, cudaStream_t);
+template int launch_rcp_table<float>(const double*, Cx<float>*, int64_t, cudaStream_t);
 
 template int launch_spectral_aux<double>(const SpectralParams<double>&, int, int, const void*, const uint8_t*, void*, cudaStream_t);
 template int launch_spectral_aux<float>(const SpectralParams<float>&, int, int, const void*, const uint8_t*, void*, cudaStream_t);

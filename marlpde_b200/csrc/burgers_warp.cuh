@@ -200,16 +200,17 @@ struct BurgersWarp {
         int i_tap[P][2][2];
         T w_tap[P][2][2];
         if (sparse_actions) {
+            // the two points of a lane's register (n = 2 j, 2 j + 1) have their taps next to each other in the tables:
+            // one 16-byte load of indices and two of weights per register instead of eight scalar loads
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = 2 * (p * TS + tl) + h;
-                    i_tap[p][h][0] = prm.tap_idx[2 * n];
-                    i_tap[p][h][1] = prm.tap_idx[2 * n + 1];
-                    w_tap[p][h][0] = prm.tap_w[2 * n];
-                    w_tap[p][h][1] = prm.tap_w[2 * n + 1];
-                }
+            for (int p = 0; p < P; ++p) {
+                const int j = p * TS + tl;
+                const int4 ti = *reinterpret_cast<const int4*>(prm.tap_idx + 4 * j);
+                i_tap[p][0][0] = ti.x; i_tap[p][0][1] = ti.y; i_tap[p][1][0] = ti.z; i_tap[p][1][1] = ti.w;
+                const Cx<T> wa = ldcx(reinterpret_cast<const Cx<T>*>(prm.tap_w) + 2 * j);
+                const Cx<T> wb = ldcx(reinterpret_cast<const Cx<T>*>(prm.tap_w) + 2 * j + 1);
+                w_tap[p][0][0] = wa.re; w_tap[p][0][1] = wa.im; w_tap[p][1][0] = wb.re; w_tap[p][1][1] = wb.im;
+            }
         }
         pdl_wait();
         pdl_launch_dependents();
@@ -256,8 +257,9 @@ struct BurgersWarp {
             const int64_t row = iout + nsub < prm.ek_rows ? iout + nsub : prm.ek_rows - 1;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                ek_pre[p] = (T)prm.ek_ref[(ref * prm.ek_rows + row) * H + kk[p]];
-                rk_pre[p] = prm.ek_rcp[(ref * prm.ek_rows + row) * H + kk[p]];
+                const Cx<T> er = ldcx(prm.ek_pair + (ref * prm.ek_rows + row) * H + kk[p]);      // (E_ref, 1 / E_ref)
+                ek_pre[p] = er.re;
+                rk_pre[p] = er.im;
             }
             kprev_pre = prm.kprev[ec];
         }

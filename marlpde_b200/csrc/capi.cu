@@ -83,7 +83,7 @@ template <typename T>
 struct Env : mpde_env {
     SpectralParams<T> prm{};
     std::vector<void*> owned;
-    T* ek_rcp_buf = nullptr;        // reciprocals of the spectrum reference (set_spectrum_ref)
+    Cx<T>* ek_rcp_buf = nullptr;    // (value, reciprocal) pairs of the spectrum reference (set_spectrum_ref)
     int64_t ek_rcp_cap = 0;
     int n_forcing = 0;
 
@@ -271,9 +271,9 @@ struct Env : mpde_env {
         // the caller's table may have been produced on any stream and step kernels may be in flight on others)
         const int64_t n = (ek && nref > 0 && rows > 0) ? nref * rows * (cfg.N / 2) : 0;
         if (n > ek_rcp_cap) {
-            T* buf = nullptr;
+            Cx<T>* buf = nullptr;
             CU(cudaDeviceSynchronize());
-            CU(cudaMalloc(&buf, (size_t)n * sizeof(T)));
+            CU(cudaMalloc(&buf, (size_t)n * sizeof(Cx<T>)));
             if (ek_rcp_buf) {
                 owned.erase(std::remove(owned.begin(), owned.end(), static_cast<void*>(ek_rcp_buf)), owned.end());
                 cudaFree(ek_rcp_buf);
@@ -288,7 +288,7 @@ struct Env : mpde_env {
             CU(cudaDeviceSynchronize());
         }
         prm.ek_ref = ek;
-        prm.ek_rcp = n > 0 ? ek_rcp_buf : nullptr;
+        prm.ek_pair = n > 0 ? ek_rcp_buf : nullptr;
         prm.ek_rows = rows;
         prm.ek_map = map;
         return 0;

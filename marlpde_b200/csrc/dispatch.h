@@ -23,7 +23,7 @@ template <typename T>
 int launch_spectral_aux_cta(const SpectralParams<T>& p, int equation, int mode, const void* src, const uint8_t* mask,
                             void* dst, cudaStream_t st);
 template <typename T> int launch_ks(const SpectralParams<T>& p, cudaStream_t st);
-template <typename T> int launch_rcp_table(const double* in, T* out, int64_t n, cudaStream_t st);
+template <typename T> int launch_rcp_table(const double* in, Cx<T>* out, int64_t n, cudaStream_t st);
 template <typename T>
 int launch_handoff(const void* vsrc, int nsrc_points, const double* ksrc, const int* src_map, const double* offset,
                    const uint8_t* mask, void* out, int64_t B, int N, cudaStream_t st);

@@ -73,8 +73,9 @@ struct SpectralParams {
     T* reward_out;          // [B][A]
     // references
     const double* ek_ref;   // [nref][ek_rows][N/2] time-averaged DNS spectrum rows
-    const T* ek_rcp;        // same shape: T(1) / T(ek_ref), filled by the library when the reference is set (step kernels
-                            // turn the reward's divisions into correction steps, common.cuh: div_by_rcp)
+    const Cx<T>* ek_pair;   // same shape: (T(ek_ref), T(1) / T(ek_ref)), filled by the library when the reference is set: one
+                            // 16-byte load per wavenumber, and the reward's divisions become correction steps
+                            // (common.cuh: div_by_rcp)
     int64_t ek_rows;
     const int* ek_map;      // [B] env -> ref index (nullptr: all use 0)
     const T* truth;         // [ntruth][truth_rows][N] DNS truth interpolated on the env grid
