@@ -540,7 +540,10 @@ def gpu_arm(args):
     pipe = HostPipeline(envs[:depth], NSUB, post_step=publish if fused else None)
     for k in range(depth):
         pipe.act_host[k].copy_(acts_host[k])
-    Ke = max(depth, min(K, 40 * depth))      # <= 40 RL steps per batch: the forced LES stays bounded for ~50
+    # e2e steps: at least 10 per batch in flight -- a 20-step run with 8 batches in flight would time the fill and the
+    # drain of the pipeline, not its rate -- and at most 40 per batch (the forced LES stays bounded for ~50); reported
+    # as e2e.steps
+    Ke = min(max(K, 10 * depth), 40 * depth)
     checksum = 0.0
 
     def e2e_round(n):
@@ -630,7 +633,8 @@ def gpu_arm(args):
                     "us_per_step": e2e_s / Ke * 1e6, "pcie_floor_us_per_step": floor_us,
                     "cores_per_rank": cores_per_rank,
                     "note": "per RL step of a batch: pinned host actions -> H2D -> step_n -> D2H state+reward -> host waits; "
-                            "independent batches overlap (HostPipeline)" +
+                            "independent batches overlap (HostPipeline); timed over `steps` = min(max(K, 10 x batches in "
+                            "flight), 40 x batches in flight) RL steps, so that a short K does not time the pipeline's fill and drain" +
                             ("; multi-GPU: rows also stored into every rank's gather buffer, each rank publishes behind its step, "
                              "only the learner rank (0) waits for the peers" if fused else "")},
             "gpu_launches": int(launches),
