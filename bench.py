@@ -561,8 +561,8 @@ def gpu_arm(args):
         if learner is not None:
             learner.synchronize()
 
-    e2e_round(3 * depth)
-    sync()
+    e2e_round(max(3 * depth, Ke))       # untimed: graph captures of every slot, host caches and clocks settled
+    new_episode()                       # the timed round starts from fresh episodes (<= 40 RL steps per batch)
     t0 = time.perf_counter()
     e2e_round(Ke)
     torch.cuda.synchronize()

@@ -131,7 +131,10 @@ int mpde_set_etdrk4(mpde_env* env, const double* E, const double* E2, const doub
 int mpde_set_forcing(mpde_env* env, const double* coef_host, int64_t n);
 
 /* Spectral-reward reference (burger_environment.py:174): DEVICE double [nref, rows, N/2] rows of
- * dns.Ek_ktt[:, :N/2]; env_map DEVICE int32 [B] or NULL (all environments use reference 0). */
+ * dns.Ek_ktt[:, :N/2]; env_map DEVICE int32 [B] or NULL (all environments use reference 0).
+ * Set-up call: synchronises the device and builds a library-owned table of (value, reciprocal) pairs from ek_dev as it is
+ * NOW (the step kernels read that table; call again after changing ek_dev).  ek_dev itself must stay valid as well (the
+ * KS and CTA-resident kernels read it directly). */
 int mpde_set_spectrum_ref(mpde_env* env, const double* ek_dev, int64_t nref, int64_t rows, const int32_t* env_map_dev);
 
 /* setGroundTruth + getMseReward (Burger.py:322-323, 578-601): DEVICE real [ntruth, rows, N] table of
