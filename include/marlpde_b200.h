@@ -275,6 +275,11 @@ int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs,
  * bound (the kernel writes the rows there -- through the multicast address when one is bound -- and the D2H copy reads
  * the copy of the current parity).  local_reward = local_state + B*S for the packed single-copy path. */
 int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward);
+/* How the single-agent state rows travel in the fused gather: on != 0 (default) = staged through shared memory and written
+ * as whole rows (256 contiguous bytes per 16 lanes: the NVLink write efficiency an 8-GPU gather into one learner needs:
+ * 0.53 -> 0.60-0.66 TB/s of ingress); 0 = every lane stores its own 16-byte pieces to every destination (shorter epilogue:
+ * 7.9 instead of 8.1 us per step on 2 GPUs, where the links are not the bound).  Sticky across mpde_set_peer_output. */
+int mpde_set_peer_row_stores(mpde_env* env, int32_t on);
 int mpde_peer_signal_next(void* const* flag_ptrs, int32_t n, void* step_dev, void* stream);
 int mpde_peer_wait_next(const void* my_flags_dev, int32_t nranks, void* expect_dev, void* err, int64_t timeout_us, void* stream);
 /* signal_next + wait_next as ONE kernel launch */

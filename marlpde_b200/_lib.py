@@ -77,6 +77,7 @@ SIGNATURES = {
     "mpde_peer_join": (C.c_int, [_vp, _vp]),
     "mpde_set_peer_output": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp), _i64, _vp, _vp]),
     "mpde_set_peer_local": (C.c_int, [_vp, _vp, _vp]),
+    "mpde_set_peer_row_stores": (C.c_int, [_vp, C.c_int32]),
     "mpde_peer_signal_next": (C.c_int, [C.POINTER(_vp), _i32, _vp, _vp]),
     "mpde_peer_exchange_next": (C.c_int, [C.POINTER(_vp), _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "mpde_peer_wait_next": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp]),

@@ -693,14 +693,31 @@ struct BurgersWarp {
                 }
                 if (!live) ra[p] = rb[p] = ii;
             }
-            if (prm.peer.mc_state == nullptr && prm.peer.n_data == 0) {
-                // one GPU: every lane stores its own points (a team covers 64 contiguous bytes per store instruction)
+            const bool gather = prm.peer.mc_state != nullptr || prm.peer.n_data > 0;
+            if (!gather || !prm.peer.row_stores) {
+                // every lane stores its own points (a team covers 64 contiguous bytes per store instruction): one GPU, or a
+                // gather whose links are not the bound
                 if (has) {
-                    Cx<T>* const row = reinterpret_cast<Cx<T>*>(state_out + e * ((int64_t)2 << rl_shift));
+                    const int64_t off = e * ((int64_t)2 << rl_shift);                       // row start, in T
+                    auto put = [&](T* base) {
+                        Cx<T>* const row = reinterpret_cast<Cx<T>*>(base + off);
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        stcx(row + p * TS + tl, ra[p]);
-                        if (ver != 0) stcx(row + H + p * TS + tl, rb[p]);
+                        for (int p = 0; p < P; ++p) {
+                            stcx(row + p * TS + tl, ra[p]);
+                            if (ver != 0) stcx(row + H + p * TS + tl, rb[p]);
+                        }
+                    };
+                    if (prm.peer.mc_state) {
+                        Cx<T>* const row = reinterpret_cast<Cx<T>*>(static_cast<T*>(prm.peer.mc_state) + poff + off);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            st_multicast(row + p * TS + tl, ra[p]);
+                            if (ver != 0) st_multicast(row + H + p * TS + tl, rb[p]);
+                        }
+                    } else {
+                        put(state_out);
+#pragma unroll 1
+                        for (int q = 0; q < prm.peer.n_data; ++q) put(static_cast<T*>(prm.peer.state[q]) + poff);
                     }
                 }
             } else {

@@ -58,6 +58,7 @@ struct mpde_env {
     virtual int set_peer_output(int n_data, void* const* state, void* const* reward, int64_t parity_stride, void* mc_state,
                                 void* mc_reward) = 0;
     virtual int set_peer_local(void* state, void* reward) = 0;
+    virtual int set_peer_row_stores(int on) = 0;
     virtual int set_peer_sync(void* const* flag_slots, int n, void* step_dev, const void* my_flags, int nranks, void* expect_dev,
                               void* err, int64_t timeout_us) = 0;
     virtual int step_fused(const void* actions, int nsub, void* state_out, void* reward_out, int async, cudaStream_t st) = 0;
@@ -328,6 +329,7 @@ struct Env : mpde_env {
             ps.reward[i] = reward[i];
         }
         ps.parity_stride = parity_stride;
+        ps.row_stores = peer_row_stores;
         if (mc_state && !mc_reward) return fail("set_peer_output: multicast of the state without the reward");
         if (mc_reward && !mc_state && n_data > 0) return fail("set_peer_output: reward-only multicast takes n_data = 0");
         ps.mc_state = mc_state;
@@ -341,6 +343,12 @@ struct Env : mpde_env {
     int set_peer_local(void* state, void* reward) override {
         peer_local_state = static_cast<T*>(state);
         peer_local_reward = static_cast<T*>(reward);
+        return 0;
+    }
+    int peer_row_stores = 1;    // PeerSink::row_stores of the next / current binding
+    int set_peer_row_stores(int on) override {
+        peer_row_stores = on ? 1 : 0;
+        prm.peer.row_stores = peer_row_stores;
         return 0;
     }
     bool peer_bound = false;
@@ -436,6 +444,8 @@ struct Env : mpde_env {
             if (!state_out || !reward_out)
                 return fail("step: a fused peer gather is bound (mpde_set_peer_output): an advancing call must write state and reward");
             p.peer.parity = (int)(peer_steps & 1);
+            static const int row_override = [] { const char* e = std::getenv("MPDE_PEER_ROW_STORES"); return e ? std::atoi(e) : -1; }();
+            if (row_override >= 0) p.peer.row_stores = row_override;       // tuning experiments
         }
         if (reward_out && nsub > 0) {
             if (cfg.reward_mode == MPDE_REWARD_SPECTRAL && !p.ek_ref) return fail("step: spectral reward without mpde_set_spectrum_ref");
@@ -850,6 +860,10 @@ int mpde_set_peer_output(mpde_env* env, int32_t n_data, void* const* state_ptrs,
 int mpde_set_peer_local(mpde_env* env, void* local_state, void* local_reward) {
     if (env) ++env->epoch;
     return env ? env->set_peer_local(local_state, local_reward) : fail("null argument");
+}
+int mpde_set_peer_row_stores(mpde_env* env, int32_t on) {
+    if (env) ++env->epoch;
+    return env ? env->set_peer_row_stores(on) : fail("null argument");
 }
 int mpde_set_peer_sync(mpde_env* env, void* const* flag_ptrs, int32_t n, void* step_dev, const void* my_flags_dev, int32_t nranks,
                        void* expect_dev, void* err, int64_t timeout_us) {

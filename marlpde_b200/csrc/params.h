@@ -41,6 +41,10 @@ struct PeerSink {
     // the per-peer loop.
     void* mc_state = nullptr;
     void* mc_reward = nullptr;
+    // single-agent state rows: 1 = staged through shared memory and written as whole rows (256 contiguous bytes per 16
+    // lanes: what the NVLink write efficiency of an 8-GPU gather wants), 0 = every lane stores its own 16-byte pieces
+    // to every destination (shorter epilogue; 64-byte segments per 4-lane team)
+    int row_stores = 1;
 };
 
 template <typename T>

@@ -186,13 +186,22 @@ class PeerGather:
         self._check(self._lib.mpde_peer_wait(self._my_flags, self.ws, self.step, self._err_ptr, self.timeout_us,
                                              self._stream()))
 
-    def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True, learner=None):
+    def fuse(self, env, n_local, S, A, use_multicast=True, gather_state=True, learner=None, row_stores=None):
         """Let ``env``'s step kernel write its [n_local,S] state and [n_local,A] reward straight into this rank's slab
         of every rank's buffer and publish the step itself (no put kernel, no NCCL).
 
         ``learner=r``: GATHER instead of all-gather -- every rank stores its rows locally and into rank r's buffer only
         (plain peer stores over NVLink); rank r waits for all ranks, the others only publish.  At 8 GPUs an all-gather
-        makes every rank ingest 8 slabs per step, a gather only the learner ("gather-style semantics suffice")."""
+        makes every rank ingest 8 slabs per step, a gather only the learner ("gather-style semantics suffice").
+
+        ``row_stores``: how single-agent state rows are written (``mpde_set_peer_row_stores``): whole 256-byte rows staged
+        through shared memory (what the ingress-bound gather of 6 and more ranks wants) or direct 16-byte pieces per lane
+        (shorter epilogue; faster while the links are not the bound).  Default: by the number of ranks."""
+        if row_stores is None:
+            row_stores = self.ws > 4
+        rc = self._lib.mpde_set_peer_row_stores(env._h, 1 if row_stores else 0)
+        if rc != 0:
+            raise RuntimeError("marlpde_b200: " + self._lib.mpde_last_error().decode())
         C = self._C
         assert n_local * (S + A) == self.chunk_elems
         slab = self.rank * self.chunk_bytes

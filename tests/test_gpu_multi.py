@@ -30,6 +30,9 @@ def _worker(rank, ws, port, q, transport="nccl"):
     if transport == "fused-ipc":            # force the CUDA-IPC / unicast path (the default tries NVSwitch multicast)
         os.environ["MPDE_PEER_BACKEND"] = "ipc"
         transport = "fused"
+    if transport.endswith("-rows"):         # whole-row state stores staged through shared memory (the default from 6 ranks up)
+        os.environ["MPDE_PEER_ROW_STORES"] = "1"
+        transport = transport[:-5]
     from marlpde_b200 import dist as mdist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -54,10 +57,11 @@ def _worker(rank, ws, port, q, transport="nccl"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused", "fused-ipc", "fused-learner"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "fused", "fused-ipc", "fused-learner", "fused-rows", "fused-learner-rows"])
 def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
     import torch.multiprocessing as mp
-    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100, "fused-ipc": 150, "fused-learner": 250}[transport]
+    ws, port = 2, 29500 + os.getpid() % 400 + {"nccl": 0, "p2p": 50, "fused": 100, "fused-ipc": 150, "fused-learner": 250,
+                                               "fused-rows": 300, "fused-learner-rows": 350}[transport]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q, transport)) for r in range(ws)]
@@ -73,7 +77,7 @@ def test_two_gpu_shards_equal_one_gpu_bitwise(transport):
         st, rw = env.step_n(a, 10)
     for o in outs:
         rows = slice(0, B)
-        if transport == "fused-learner" and o[0] != 0:      # a non-learner rank only holds its own rows
+        if transport.startswith("fused-learner") and o[0] != 0:      # a non-learner rank only holds its own rows
             rows = slice(o[0] * B // ws, (o[0] + 1) * B // ws)
         assert np.array_equal(o[1][rows], st.cpu().numpy()[rows])
         assert np.array_equal(o[2][rows], rw.cpu().numpy()[rows])
