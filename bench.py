@@ -546,12 +546,16 @@ def gpu_arm(args):
     Ke = min(max(K, 10 * depth), 40 * depth)
     checksum = 0.0
 
+    stamps = []
+
     def e2e_round(n):
         nonlocal checksum
+        stamps.clear()
         for i in range(n):
             k = i % depth
             st_h, rw_h = pipe.collect(k)              # results of this batch's previous step are on the host
             checksum += float(rw_h[0, 0])             # the host really reads them
+            stamps.append(time.perf_counter())
             pipe.submit(k)                            # next actions for this batch (already in pinned memory)
             if learner is not None:
                 learner.wait_event(pipe.done[k])
@@ -567,6 +571,9 @@ def gpu_arm(args):
     e2e_round(Ke)
     torch.cuda.synchronize()
     e2e_local = time.perf_counter() - t0
+    # rate inside the round (host time stamps at every collect): first and second half, in us per step
+    half = len(stamps) // 2
+    e2e_halves = [round((stamps[half] - stamps[0]) / half * 1e6, 2), round((stamps[-1] - stamps[half]) / (len(stamps) - 1 - half) * 1e6, 2)] if half > 1 else None
     sync()
     e2e_s = e2e_local
     clocks = sampler.stop() if sampler else None
@@ -630,7 +637,7 @@ def gpu_arm(args):
             "e2e": {"value": total_envs * NSUB * Ke / e2e_s, "unit": "env-steps/s",
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": Ke, "batches_in_flight": depth, "us_per_step_per_rank": per_rank_e2e,
-                    "us_per_step": e2e_s / Ke * 1e6, "pcie_floor_us_per_step": floor_us,
+                    "us_per_step": e2e_s / Ke * 1e6, "us_per_step_first_second_half": e2e_halves, "pcie_floor_us_per_step": floor_us,
                     "cores_per_rank": cores_per_rank,
                     "note": "per RL step of a batch: pinned host actions -> H2D -> step_n -> D2H state+reward -> host waits; "
                             "independent batches overlap (HostPipeline); timed over `steps` = min(max(K, 10 x batches in "
