@@ -547,14 +547,15 @@ def gpu_arm(args):
     checksum = 0.0
 
     stamps = []
+    rw_np = [r.numpy() for r in pipe.reward_host]     # numpy views of the pinned result buffers
 
     def e2e_round(n):
         nonlocal checksum
         stamps.clear()
         for i in range(n):
             k = i % depth
-            st_h, rw_h = pipe.collect(k)              # results of this batch's previous step are on the host
-            checksum += float(rw_h[0, 0])             # the host really reads them
+            pipe.collect(k)                           # results of this batch's previous step are on the host
+            checksum += float(rw_np[k][0, 0])         # the host really reads them
             stamps.append(time.perf_counter())
             pipe.submit(k)                            # next actions for this batch (already in pinned memory)
             if learner is not None:

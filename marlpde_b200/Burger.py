@@ -377,6 +377,29 @@ class Burger(SpectralEnv):
             self.t += self.dt
         self._state_at = self._reward_at = -1
 
+    def host_step_closure(self, actions_host, n, packed_out, stream):
+        """``step_n_host(actions_host, n, ..., packed_out=packed_out, stream=stream)`` with everything that does not change
+        between calls resolved once: returns a zero-argument callable for a learner's inner loop (one ctypes call into
+        ``mpde_step_host_packed`` + the host counters; about a third of the Python time of ``step_n_host``)."""
+        for t_ in (actions_host, packed_out):
+            assert not t_.is_cuda and t_.is_contiguous() and t_.dtype == self.dtype
+        assert self._spec_ref is not None or self._truth_shift is not None
+        assert packed_out.numel() == self.nenvs * (self._state_size + self._reward_buf.shape[1])
+        fn, h, n = self._lib.mpde_step_host_packed, self._h, int(n)
+        a_ptr, o_ptr, st, dt = actions_host.data_ptr(), packed_out.data_ptr(), stream.cuda_stream, self.dt
+
+        def go():
+            if self._forcing_dirty:
+                self._upload_forcing()
+            if fn(h, a_ptr, n, o_ptr, st) != 0:
+                L_check(-1)
+            self.stepnum += n
+            self.ioutnum += n
+            for _ in range(n):
+                self.t += dt
+            self._state_at = self._reward_at = -1
+        return go
+
     def step(self, actions=None):
         """Burger.py:333-499: one solver step."""
         self.step_n(actions, 1, want_state=False, want_reward=self._truth_shift is not None)
