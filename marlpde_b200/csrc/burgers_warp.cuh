@@ -782,16 +782,16 @@ struct BurgersWarp {
             const int tail = (ver == 3 || ver == 4) ? N / 2 : 0;
             const int RL = nf * seg + tail;
             const int S = A * RL;
-            // (a, r) = (agent, position inside the agent's row) of output number o = a RL + r, by a multiply-shift division:
-            // exact while o RL < 2^22 (here o < S <= 2.5 N and RL <= 2.5 N, N <= 256) -- an integer division per element would
-            // cost more than the ten solver steps' worth of state arithmetic at A = N, and an incremental (a, r) needs
-            // divergent loops
-            static_assert(N <= 256, "multiply-shift (a, r) split assumes S * RL < 2^22 and S * 2^22 / 3 < 2^32");
+            // (a, r) = (agent, position inside the agent's row) of output number o = a RL + r, by a multiply-high division:
+            // floor(o m / 2^32) with m = floor(2^32 / RL) + 1 is exact while o RL < 2^32 (here o < S = A RL <= 33536 and
+            // RL <= 640 for N <= 256; RL >= 3, so m fits 32 bits) -- an integer division per element would cost more than
+            // the ten solver steps' worth of state arithmetic at A = N, and an incremental (a, r) needs divergent loops
+            static_assert(N <= 256, "multiply-high (a, r) split assumes S * RL < 2^32");
             const int npa = A == 1 ? N : N / A;
-            const unsigned magic = (1u << 22) / (unsigned)RL + 1u;
+            const unsigned magic = (unsigned)(0x100000000ull / (unsigned long long)RL) + 1u;
             const int nfseg = nf * seg, start0 = A == 1 ? N : N - 1;
             auto element = [&](int o) {
-                const int a = (int)(((unsigned)o * magic) >> 22), r = o - a * RL;
+                const int a = (int)__umulhi((unsigned)o, magic), r = o - a * RL;
                 int idx;
                 if (r < nfseg) {
                     const int fld = r >= seg ? 1 : 0;
