@@ -724,6 +724,9 @@ def batch_sweep(torch, device):
     return out
 
 
+OTHER_CHAINS = int(os.environ.get("MPDE_OTHER_CHAINS", "2"))     # independent batches in flight for configurations 3 and 5 (4 measures the same)
+
+
 def other_configs(torch, device, only=None):
     """BASELINE configs[2], [3], [4] on one GPU, measured in-process after the headline (each < 1 s of GPU time)."""
     from marlpde_b200 import Burger, KS
@@ -734,13 +737,13 @@ def other_configs(torch, device, only=None):
     # ---- C3: KS L=22 N=64 x 8192, M=64 hat basis, 10 ETDRK4 steps + state per launch
     B, n, m = 8192, 64, 64
     pool = [KS(L=22, N=n, dt=0.25, nsteps=100000, nenvs=B, u0=rng.normal(0, 1e-3, (B, n)), history=False, device=device)
-            for _ in range(6)]
+            for _ in range(8)]
     for k in pool:
         k.setup_basis(m, "hat")
     a = torch.as_tensor(rng.normal(0, 1e-3, (B, m)), device=device)
 
-    ms = time_graph(torch, [(lambda k=k: k.step_n(a, 10, want_reward=False)) for k in pool], chains=2)
-    res["c3_ks_n64_x8192"] = {"launch_us": ms * 1e3, "batches_in_flight": 2, "value": B * 10 / (ms * 1e-3), "unit": "env-steps/s", "n_sub": 10,
+    ms = time_graph(torch, [(lambda k=k: k.step_n(a, 10, want_reward=False)) for k in pool], chains=OTHER_CHAINS)
+    res["c3_ks_n64_x8192"] = {"launch_us": ms * 1e3, "batches_in_flight": OTHER_CHAINS, "value": B * 10 / (ms * 1e-3), "unit": "env-steps/s", "n_sub": 10,
                               "hbm_frac": B * BYTES_KS / (ms * 1e-3) / 1e9 / peak,
                               "fp64_frac": B * 10 * FLOPS_KS_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
                               "alive": all(int((k.status != 0).sum()) == 0 for k in pool)}
@@ -779,11 +782,11 @@ def other_configs(torch, device, only=None):
     torch.cuda.empty_cache()
     # ---- C5 per GPU: MARL Burgers N=32 x 8192, 32 agents, MSE reward, 4-lane teams
     B = 8192
-    pool = [make_batch_c5(torch, device, 42 + i, B=B) for i in range(10)]
+    pool = [make_batch_c5(torch, device, 42 + i, B=B) for i in range(12)]
     a5 = torch.as_tensor(rng.uniform(0.0, 0.02, (B, M)), device=device)
 
-    ms = time_graph(torch, [(lambda e=e: e.step_n(a5, NSUB)) for e in pool], chains=2)
-    res["c5_marl_n32_x8192_per_gpu"] = {"launch_us": ms * 1e3, "batches_in_flight": 2, "value": B * NSUB / (ms * 1e-3), "unit": "env-steps/s", "n_sub": NSUB,
+    ms = time_graph(torch, [(lambda e=e: e.step_n(a5, NSUB)) for e in pool], chains=OTHER_CHAINS)
+    res["c5_marl_n32_x8192_per_gpu"] = {"launch_us": ms * 1e3, "batches_in_flight": OTHER_CHAINS, "value": B * NSUB / (ms * 1e-3), "unit": "env-steps/s", "n_sub": NSUB,
                                         "hbm_frac": B * BYTES_C5 / (ms * 1e-3) / 1e9 / peak,
                                         "fp64_frac": B * NSUB * FLOPS_PER_ENV_STEP / (ms * 1e-3) / 1e12 / fp64_peak,
                                         "alive": all(int((e.status != 0).sum()) == 0 for e in pool)}
