@@ -120,3 +120,34 @@ def test_truth_interpolant_follows_interp2d_semantics(golden):
     assert row.shape == (32,)
     assert np.allclose(row, f.rows(x, [0.1])[0])
     assert f(x, [0.0, 0.1]).shape == (2, 32)
+
+
+def test_kernel_integer_and_division_identities():
+    """Two arithmetic identities the step kernels rely on (csrc/burgers_warp.cuh, csrc/common.cuh), restated exactly:
+    (1) the (agent, position) split of the state gather, floor(o m / 2^32) with m = floor(2^32 / RL) + 1, equals o // RL for
+        every state layout the warp kernels accept (N <= 256, any agent count dividing N, state versions 0..4);
+    (2) a / b computed as q0 + (a - q0 b) y with y = RN(1 / b), q0 = RN(a y) and fused multiply-adds is the correctly
+        rounded quotient (the reward's divisions use reciprocals prepared ahead of time)."""
+    from fractions import Fraction
+    import random
+    for N in (8, 16, 32, 64, 128, 256):
+        for A in [a for a in range(1, N + 1) if N % a == 0]:
+            for ver in range(5):
+                nf = 2 if ver in (1, 2) else 1
+                seg = N if A == 1 else N // A + 2
+                RL = nf * seg + (N // 2 if ver in (3, 4) else 0)
+                m = (1 << 32) // RL + 1
+                assert m < (1 << 32)
+                o = np.arange(A * RL + 1, dtype=np.uint64)
+                assert np.array_equal((o * np.uint64(m)) >> np.uint64(32), o // np.uint64(RL)), (N, A, ver)
+
+    def fma(x, y, z):
+        return float(Fraction(x) * Fraction(y) + Fraction(z))       # one rounding
+
+    rnd = random.Random(7)
+    for _ in range(20000):
+        b = rnd.choice([float(rnd.randint(1, 6000)), 15.0, rnd.uniform(1, 2) * 10 ** rnd.uniform(-12, 3)])
+        a = rnd.choice([0.0, float(np.float32(rnd.uniform(0, 1) * 10 ** rnd.uniform(-12, 2))), rnd.uniform(0, 2) * 10 ** rnd.uniform(-14, 5)])
+        y = 1.0 / b
+        q0 = a * y
+        assert fma(fma(-q0, b, a), y, q0) == a / b, (a, b)
