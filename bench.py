@@ -537,7 +537,11 @@ def gpu_arm(args):
         gathers[k].signal_next()
         return None
 
-    pipe = HostPipeline(envs[:depth], NSUB, post_step=publish if fused else None)
+    def publish_on(k, stream):
+        gathers[k].step += 1
+        gathers[k].signal_next(stream)
+
+    pipe = HostPipeline(envs[:depth], NSUB, post_step=publish if fused else None, post_step_on=publish_on if fused else None)
     for k in range(depth):
         pipe.act_host[k].copy_(acts_host[k])
     # e2e steps: at least 10 per batch in flight -- a 20-step run with 8 batches in flight would time the fill and the
@@ -560,8 +564,7 @@ def gpu_arm(args):
             pipe.submit(k)                            # next actions for this batch (already in pinned memory)
             if learner is not None:
                 learner.wait_event(pipe.done[k])
-                with torch.cuda.stream(learner):
-                    gathers[k].wait_next()
+                gathers[k].wait_next(learner)
         pipe.drain()
         if learner is not None:
             learner.synchronize()

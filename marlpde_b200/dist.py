@@ -150,6 +150,7 @@ class PeerGather:
         self.gathered = self._all[0]
         self._item = item
         self._steps_dev = torch.zeros(4, dtype=torch.int64, device=self.device)    # [0] published, [1] awaited
+        self._steps_ptr, self._expect_ptr = self._steps_dev.data_ptr(), self._steps_dev.data_ptr() + 8
         self._fused = None
         self.learner = None
         self._wait_flags, self._wait_n, self._n_slots = self._my_flags, self.ws, self.ws
@@ -167,8 +168,9 @@ class PeerGather:
         if rc != 0:
             raise RuntimeError("marlpde_b200 peer: " + self._lib.mpde_peer_last_error().decode())
 
-    def _stream(self):
-        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    def _stream(self, stream=None):
+        """``stream``: a torch stream (or None = the current stream of this device)."""
+        return self._C.c_void_p((stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream)
 
     def put(self, src):
         """Store this rank's slab into every rank's buffer and publish the step.  With ``copies=2`` step s lands in copy
@@ -256,20 +258,21 @@ class PeerGather:
         self._fused = env
         env._state_at = env._reward_at = -1
 
-    def signal_next(self):
+    def signal_next(self, stream=None):
         """Enqueue (behind the step kernel in stream order) the publication of one more step to every rank."""
-        self._check(self._lib.mpde_peer_signal_next(self._flag_slots, self._n_slots, self._steps_dev.data_ptr(), self._stream()))
+        self._check(self._lib.mpde_peer_signal_next(self._flag_slots, self._n_slots, self._steps_ptr, self._stream(stream)))
 
     def exchange_next(self):
         """signal_next() + wait_next() as one kernel launch."""
-        self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self._n_slots, self._steps_dev.data_ptr(), self._wait_flags,
-                                                      self._wait_n, self._steps_dev[1:].data_ptr(), self._err_ptr, self.timeout_us,
+        self._check(self._lib.mpde_peer_exchange_next(self._flag_slots, self._n_slots, self._steps_ptr, self._wait_flags,
+                                                      self._wait_n, self._expect_ptr, self._err_ptr, self.timeout_us,
                                                       self._stream()))
 
-    def wait_next(self):
-        """Current stream waits until every rank has published one more step than the last wait_next() saw."""
-        self._check(self._lib.mpde_peer_wait_next(self._wait_flags, self._wait_n, self._steps_dev[1:].data_ptr(), self._err_ptr,
-                                                  self.timeout_us, self._stream()))
+    def wait_next(self, stream=None):
+        """The stream (default: the current one) waits until every rank has published one more step than the last
+        wait_next() saw."""
+        self._check(self._lib.mpde_peer_wait_next(self._wait_flags, self._wait_n, self._expect_ptr, self._err_ptr,
+                                                  self.timeout_us, self._stream(stream)))
 
     def current(self):
         """[world_size, chunk_elems] copy written by step number ``self.step`` (1-based host count of fused steps)."""

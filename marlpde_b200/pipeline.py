@@ -11,9 +11,12 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, envs, n_sub, post_step=None):
+    def __init__(self, envs, n_sub, post_step=None, post_step_on=None):
         self.envs, self.n_sub = list(envs), int(n_sub)
         self.post_step = post_step          # e.g. the all-gather to the learner rank, enqueued after the step
+        # post_step_on(k, stream): the same hook for callers that enqueue on an explicit stream -- used instead of
+        # post_step(k, None, None) on the pre-bound path, without making the slot's stream current first
+        self.post_step_on = post_step_on
         e0 = self.envs[0]
         dev, dt = e0.device, e0.dtype
         B, M, S, A = e0.nenvs, e0.M, e0._state_buf.shape[1], e0._reward_buf.shape[1]
@@ -42,7 +45,9 @@ class HostPipeline:
         go = self._fast[k]
         if go is not None:                      # steady state: one pre-bound library call + the event
             go()
-            if self.post_step is not None:
+            if self.post_step_on is not None:
+                self.post_step_on(k, self.streams[k])
+            elif self.post_step is not None:
                 with torch.cuda.stream(self.streams[k]):
                     self.post_step(k, None, None)
             self.done[k].record(self.streams[k])
